@@ -1,0 +1,152 @@
+"""Pin the oracle (CPU restatement) against fixtures produced by RUNNING the reference's modules
+(tests/golden/make_golden.py).  CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from amb200 import synth
+from oracle import cdm_ref, cmdm_ref, diffusion_ref as D, pointops_ref
+
+TOL = 2e-5  # fp32 noise floor of these nets is ~1e-6; the parity budget is 1e-3
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def _pe_buffers(sd, names):
+    from oracle.nn_ref import positional_table
+    for name, (L, d) in names.items():
+        sd[name] = positional_table(L, d).unsqueeze(1)
+    return sd
+
+
+def _keys(golden_dir):
+    with open(os.path.join(golden_dir, "state_keys.json")) as f:
+        return json.load(f)
+
+
+def test_tables_match_reference(golden_dir):
+    g = _load(golden_dir, "diffusion_tables.npz")
+    for T in (1000, 500):
+        # the reference always goes through SpacedDiffusion, which re-derives betas from alpha-bar even
+        # for the identity spacing (respace.py:73-87): do the same so the fp64 tables are bit-equal
+        tab = D.make_tables(D.respaced(D.cosine_betas(T), range(T))[0])
+        for k in ("betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod",
+                  "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_variance",
+                  "posterior_log_variance_clipped", "posterior_mean_coef1", "posterior_mean_coef2"):
+            np.testing.assert_array_equal(tab[k], g[f"T{T}_{k}"], err_msg=k)
+        nb, tmap = D.respaced(D.cosine_betas(T), D.space_timesteps(T, "ddim100"))
+        np.testing.assert_array_equal(np.array(tmap), g[f"T{T}_ddim100_map"])
+        np.testing.assert_array_equal(nb, g[f"T{T}_ddim100_betas"])
+        np.testing.assert_array_equal(D.make_tables(nb)["alphas_cumprod"], g[f"T{T}_ddim100_alphas_cumprod"])
+    np.testing.assert_array_equal(D.linear_betas(1000), g["linear1000_betas"])
+    np.testing.assert_array_equal(np.array(sorted(D.space_timesteps(300, [10, 15, 20]))), g["space_300_10_15_20"])
+    np.testing.assert_array_equal(np.array(sorted(D.space_timesteps(1000, "ddim50"))), g["space_1000_ddim50"])
+    # survey probes
+    tab = D.make_tables(D.cosine_betas(1000))
+    assert tab["posterior_mean_coef1"][0] == 1.0 and tab["posterior_mean_coef2"][0] == 0.0
+    assert abs(tab["posterior_variance"][1] - 2.179e-5) < 1e-8
+
+
+def test_sampler_steps_match_reference(golden_dir):
+    g = _load(golden_dir, "diffusion_steps.npz")
+    x_t, x0h, noise = (torch.from_numpy(g[k]) for k in ("x_t", "x0h", "noise"))
+    x_mask = torch.from_numpy(g["x_mask"])
+    B = x_t.shape[0]
+    tab = D.make_tables(D.cosine_betas(1000))
+    for tv in (999, 500, 1, 0):
+        out = D.p_sample_step(tab, x0h, x_t, torch.tensor([tv] * B), noise)
+        np.testing.assert_allclose(out.numpy(), g[f"p_sample_t{tv}"], rtol=0, atol=1e-6)
+    tmix = torch.from_numpy(g["t_mixed"])
+    np.testing.assert_allclose(D.p_sample_step(tab, x0h, x_t, tmix, noise).numpy(), g["p_sample_mixed"], rtol=0, atol=1e-6)
+    nb, tmap = D.respaced(D.cosine_betas(1000), D.space_timesteps(1000, "ddim100"))
+    dtab = D.make_tables(nb)
+    for tv in (99, 50, 1, 0):
+        out = D.ddim_step(dtab, x0h, x_t, torch.tensor([tv] * B), noise, eta=0.0)
+        np.testing.assert_allclose(out.numpy(), g[f"ddim_t{tv}"], rtol=0, atol=2e-5)
+        assert (g[f"ddim_model_t{tv}"] == tmap[tv]).all()  # _WrappedModel maps spaced t -> original t
+    out = D.ddim_step(dtab, x0h, x_t, torch.tensor([50] * B), noise, eta=0.5)
+    np.testing.assert_allclose(out.numpy(), g["ddim_eta05_t50"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(D.q_sample(tab, x0h, tmix, noise).numpy(), g["q_sample_mixed"], rtol=0, atol=1e-6)
+    loss = D.masked_mse(x_t, x0h, x_mask)
+    np.testing.assert_allclose(loss.numpy(), g["loss_mixed"], rtol=1e-6)
+    np.testing.assert_allclose(loss.numpy(), g["mse_mixed"], rtol=1e-6)
+
+
+def test_cdm_oracle_matches_reference(golden_dir):
+    g = _load(golden_dir, "cdm_b2_n1024.npz")
+    shapes = _keys(golden_dir)["CDM"]
+    sd = _pe_buffers(synth.fill_state_dict(shapes, seed=0), {"timestep_embedder.pe": (1000, 128)})
+    B, N = 2, 1024
+    xyz = synth.scene_points(B, N, seed=11)
+    x = torch.randn(B, N, 6, generator=torch.Generator().manual_seed(11))
+    txt = synth.text_features(B, seed=11)
+    for tag in ("a", "b"):
+        out = cdm_ref.cdm_forward(sd, x, torch.from_numpy(g[f"t_{tag}"]), txt, xyz)
+        err = (out.numpy() - g[f"out_{tag}"]).__abs__().max()
+        assert err < TOL, err
+
+
+@pytest.mark.parametrize("N", [1024, 8192])
+def test_cmdm_oracle_matches_reference(golden_dir, N):
+    g = _load(golden_dir, f"cmdm_b3_n{N}.npz")
+    shapes = _keys(golden_dir)["CMDM"]
+    sd = _pe_buffers(synth.fill_state_dict(shapes, seed=0),
+                     {"timestep_embedder.pe": (1000, 512), "positional_encoder.pe": (5000, 512)})
+    B, T, Dm = 3, 196, 263
+    xyz = synth.scene_points(B, N, seed=21, dup_frac=0.05)
+    contact = synth.contact_map(B, N, seed=21)
+    x = synth.motion_noise(B, T, Dm, seed=21)
+    x_mask = synth.motion_mask(B, T, seed=21)
+    assert (x_mask.numpy() == g["x_mask"]).all()
+    txt = synth.text_features(B, seed=21)
+    cont = cmdm_ref.contact_tokens(sd, xyz, contact)
+    assert np.abs(cont.numpy() - g["contact_tokens"]).max() < TOL
+    valid = (~x_mask).numpy()
+    for tag in ("a", "b"):
+        out = cmdm_ref.cmdm_forward(sd, x, torch.from_numpy(g[f"t_{tag}"]), txt, xyz, contact, x_mask, cont_emb=cont)
+        err = np.abs(out.numpy() - g[f"out_{tag}"])[valid].max()  # padded query rows are implementation-defined
+        assert err < TOL, err
+    if N == 1024:
+        er = torch.tensor([[True], [False], [True]])
+        mk = torch.tensor([[False], [True], [True]])
+        out = cmdm_ref.cmdm_forward(sd, x, torch.tensor([10, 20, 30]), txt, xyz, contact, x_mask, cont_emb=cont,
+                                    c_text_erase=er, c_pc_erase=mk, c_text_mask=mk, c_pc_mask=er)
+        assert np.abs(out.numpy() - g["out_erase"])[valid].max() < TOL
+        # chain with injected noise
+        tab = D.make_tables(D.cosine_betas(1000))
+        img = x.clone()
+        for si, tv in enumerate(g["chain_t"].tolist()):
+            t = torch.tensor([tv] * B)
+            x0h = cmdm_ref.cmdm_forward(sd, img, t, txt, xyz, contact, x_mask, cont_emb=cont)
+            img = D.p_sample_step(tab, x0h, img, t, synth.step_noise(img.shape, si))
+        assert np.abs(img.numpy() - g["chain_out"])[valid].max() < 1e-4
+
+
+def test_pointops_c_vs_numpy_and_fixture(golden_dir):
+    g = _load(golden_dir, "cmdm_b3_n1024.npz")
+    B, N = 3, 1024
+    xyz = synth.scene_points(B, N, seed=21, dup_frac=0.05).reshape(B * N, 3)
+    o = torch.tensor([N, 2 * N, 3 * N], dtype=torch.int32)
+    no = torch.tensor([N // 4, 2 * (N // 4), 3 * (N // 4)], dtype=torch.int32)
+    fidx = pointops_ref.furthestsampling(xyz, o, no)
+    assert (fidx.numpy() == g["fps_idx"]).all()
+    assert (fidx.numpy() == pointops_ref.fps_numpy(xyz.numpy(), o.tolist(), no.tolist())).all()
+    kidx, kd = pointops_ref.knnquery(16, xyz, xyz[fidx.long()], o, no)
+    assert (kidx.numpy() == g["knn_idx"]).all()
+    i2, d2 = pointops_ref.knn_numpy(16, xyz.numpy(), xyz[fidx.long()].numpy(), o.tolist(), no.tolist())
+    assert (kidx.numpy() == i2).all()
+    # sortedness + segment containment (size-independent properties)
+    assert (np.diff(kd.numpy(), axis=1) >= 0).all()
+    seg = np.repeat(np.arange(B), N // 4)
+    assert ((kidx.numpy() // N) == seg[:, None]).all()
+    # ragged segments + fewer than k candidates
+    xyz2 = xyz[:40]
+    o2 = torch.tensor([5, 40], dtype=torch.int32)
+    i3, _ = pointops_ref.knnquery(8, xyz2, xyz2, o2, o2)
+    assert (i3[:5, :5].numpy() < 5).all() and (i3[:5, 5:] == 0).all()
+    assert (i3[5:].numpy() >= 5).all()
