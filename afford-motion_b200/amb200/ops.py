@@ -1,0 +1,218 @@
+"""Thin torch-tensor wrappers over the C-ABI: pass raw device pointers + the current CUDA stream.
+PyTorch is only the allocator / stream provider here; every op below runs a kernel from libamb200.so."""
+from typing import Optional
+
+import torch
+
+from . import lib as _l
+
+ACT = {None: 0, "none": 0, "gelu": 1, "silu": 2, "relu": 3, "relu_after_res": 3 | 16}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _l.AmbError("amb200 ops are CUDA-only (sm_100a); got a CPU tensor — there is no CPU fallback")
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    assert t.dtype == torch.float32 and t.is_contiguous(), (t.dtype, t.is_contiguous())
+    return t
+
+
+def randn_(out: torch.Tensor, per_sample: int, nsample: int, sample0: int, seed: int, subseq: int):
+    _chk_cuda(out)
+    _l.check(_l.load().am_randn(_ptr(out), per_sample, nsample, sample0, seed, subseq, _stream()), "am_randn")
+    return out
+
+
+def p_sample_update(x0_hat, x_t, x_prev, noise, coef1, coef2, logvar, t, t_stride, seed=0, sample0=0):
+    _chk_cuda(x0_hat, x_t, x_prev, t)
+    B = x_t.shape[0]
+    per = x_t.numel() // B
+    _l.check(_l.load().am_p_sample_update(_ptr(_f32c(x0_hat)), _ptr(_f32c(x_t)), _ptr(x_prev), _ptr(noise), _ptr(coef1), _ptr(coef2),
+                                         _ptr(logvar), _ptr(t), t_stride, B, per, seed, sample0, _stream()), "am_p_sample_update")
+    return x_prev
+
+
+def ddim_update(x0_hat, x_t, x_prev, noise, sqrt_recip_ac, sqrt_recipm1_ac, ac, ac_prev, eta, t, t_stride, seed=0, sample0=0):
+    _chk_cuda(x0_hat, x_t, x_prev, t)
+    B = x_t.shape[0]
+    per = x_t.numel() // B
+    _l.check(_l.load().am_ddim_update(_ptr(_f32c(x0_hat)), _ptr(_f32c(x_t)), _ptr(x_prev), _ptr(noise), _ptr(sqrt_recip_ac),
+                                     _ptr(sqrt_recipm1_ac), _ptr(ac), _ptr(ac_prev), float(eta), _ptr(t), t_stride, B, per, seed,
+                                     sample0, _stream()), "am_ddim_update")
+    return x_prev
+
+
+def q_sample(x0, noise, x_t, sqrt_ac, sqrt_1mac, t):
+    _chk_cuda(x0, noise, x_t, t)
+    B = x0.shape[0]
+    _l.check(_l.load().am_q_sample(_ptr(_f32c(x0)), _ptr(_f32c(noise)), _ptr(x_t), _ptr(sqrt_ac), _ptr(sqrt_1mac), _ptr(t), B,
+                                  x0.numel() // B, _stream()), "am_q_sample")
+    return x_t
+
+
+def masked_mse(x0, pred, mask_u8, loss):
+    _chk_cuda(x0, pred, loss)
+    B, T, D = x0.shape
+    _l.check(_l.load().am_masked_mse(_ptr(_f32c(x0)), _ptr(_f32c(pred)), _ptr(mask_u8), _ptr(loss), B, T, D, _stream()), "am_masked_mse")
+    return loss
+
+
+def add_i32(dst, delta):
+    _l.check(_l.load().am_add_i32(_ptr(dst), int(delta), dst.numel(), _stream()), "am_add_i32")
+
+
+def linear(x, w, y, M, N, K, bias=None, act=None, residual=None, ldx=None, ldw=None, ldy=None, ldr=0, res_mod=0,
+           xmap=(0, 0, 0), ymap=(0, 0, 0)):
+    """y = act(x w^T + bias) (+ residual) on raw strided views; see am_linear_f32."""
+    _chk_cuda(x, w, y)
+    ldx = K if ldx is None else ldx
+    ldw = K if ldw is None else ldw
+    ldy = N if ldy is None else ldy
+    if residual is not None and ldr == 0:
+        ldr = N
+    _l.check(_l.load().am_linear_f32(_ptr(x), ldx, _ptr(w), ldw, _ptr(y), ldy, M, N, K, _ptr(bias), ACT[act], _ptr(residual), ldr,
+                                    res_mod, xmap[0], xmap[1], xmap[2], ymap[0], ymap[1], ymap[2], _stream()), "am_linear_f32")
+    return y
+
+
+def layernorm(x, gamma, beta, y, M, D, residual=None, eps=1e-5, ldx=None, ldy=None, ldr=None):
+    _chk_cuda(x, y)
+    _l.check(_l.load().am_layernorm(_ptr(x), D if ldx is None else ldx, _ptr(residual), D if ldr is None else ldr, _ptr(gamma),
+                                   _ptr(beta), _ptr(y), D if ldy is None else ldy, M, D, eps, _stream()), "am_layernorm")
+    return y
+
+
+def mha_fwd(qkv, out, key_pad_u8, B, S, H, hd, scale):
+    _chk_cuda(qkv, out)
+    _l.check(_l.load().am_mha_fwd(_ptr(qkv), _ptr(out), _ptr(key_pad_u8), B, S, H, hd, float(scale), _stream()), "am_mha_fwd")
+    return out
+
+
+def gather_time_token(X, S, D, row, table, t, t_stride, B):
+    _l.check(_l.load().am_gather_time_token(_ptr(X), S, D, row, _ptr(table), _ptr(t), t_stride, B, _stream()), "am_gather_time_token")
+
+
+def gather_rows(src, idx, dst, m, c):
+    _l.check(_l.load().am_gather_rows(_ptr(src), _ptr(idx), _ptr(dst), m, c, _stream()), "am_gather_rows")
+    return dst
+
+
+def furthestsampling(xyz, offset, new_offset, n_max: int, m_total: int):
+    """pointops.furthestsampling (models/scene_models/pointops.py:10-27) without the host syncs: sizes come from the caller."""
+    _chk_cuda(xyz, offset, new_offset)
+    idx = torch.empty(m_total, dtype=torch.int32, device=xyz.device)
+    tmp = torch.empty(xyz.shape[0], dtype=torch.float32, device=xyz.device) if n_max > 8192 else None
+    _l.check(_l.load().am_furthestsampling(offset.numel(), n_max, _ptr(_f32c(xyz)), _ptr(offset), _ptr(new_offset), _ptr(tmp), _ptr(idx),
+                                          _stream()), "am_furthestsampling")
+    return idx
+
+
+def knnquery(nsample, xyz, new_xyz, offset, new_offset):
+    """pointops.knnquery (pointops.py:30-45) -> (idx int32 [m,k], dist2 fp32 [m,k]; squared, caller takes sqrt if needed)."""
+    _chk_cuda(xyz, new_xyz, offset, new_offset)
+    m = new_xyz.shape[0]
+    idx = torch.empty(m, nsample, dtype=torch.int32, device=xyz.device)
+    d2 = torch.empty(m, nsample, dtype=torch.float32, device=xyz.device)
+    _l.check(_l.load().am_knnquery(offset.numel(), m, nsample, _ptr(_f32c(xyz)), _ptr(_f32c(new_xyz)), _ptr(offset), _ptr(new_offset),
+                                  _ptr(idx), _ptr(d2), _stream()), "am_knnquery")
+    return idx, d2
+
+
+def pt_layer_fwd(p, qkv, idx, w, out, n, c, k):
+    """w: dict of folded weights (see amb200.pack.pack_pt_layer)."""
+    _l.check(_l.load().am_pt_layer_fwd(_ptr(p), _ptr(qkv), _ptr(idx), _ptr(w["wp1"]), _ptr(w["bp1"]), _ptr(w["wp2"]), _ptr(w["bp2"]),
+                                      _ptr(w["bnw_s"]), _ptr(w["bnw_t"]), _ptr(w["ww1"]), _ptr(w["bw1"]), _ptr(w["ww2"]), _ptr(w["bw2"]),
+                                      _ptr(w.get("post_s")), _ptr(w.get("post_t")), _ptr(out), n, c, k, _stream()), "am_pt_layer_fwd")
+    return out
+
+
+def transition_down_fwd(p, x, new_p, idx, W, shift, out, m, cin, cout, k):
+    _l.check(_l.load().am_transition_down_fwd(_ptr(p), _ptr(x), _ptr(new_p), _ptr(idx), _ptr(W), _ptr(shift), _ptr(out), m, cin, cout, k,
+                                             _stream()), "am_transition_down_fwd")
+    return out
+
+
+def cdm_encoder_partial(x_t, xyz, w_ea, b_ea, ln_g, ln_b, qf, ldq, part, B, N, cx, nchunk):
+    _l.check(_l.load().am_cdm_encoder_partial(_ptr(x_t), _ptr(xyz), _ptr(w_ea), _ptr(b_ea), _ptr(ln_g), _ptr(ln_b), _ptr(qf), ldq,
+                                             _ptr(part), B, N, cx, nchunk, _stream()), "am_cdm_encoder_partial")
+
+
+def cdm_encoder_combine(part, z, B, nchunk):
+    _l.check(_l.load().am_cdm_encoder_combine(_ptr(part), _ptr(z), B, nchunk, _stream()), "am_cdm_encoder_combine")
+
+
+def cdm_decoder_point(x_t, xyz, wd, bd, lnq_g, lnq_b, kf, ldk, U, bo, lnm_g, lnm_b, h1, hn, B, N, cx):
+    _l.check(_l.load().am_cdm_decoder_point(_ptr(x_t), _ptr(xyz), _ptr(wd), _ptr(bd), _ptr(lnq_g), _ptr(lnq_b), _ptr(kf), ldk, _ptr(U),
+                                           _ptr(bo), _ptr(lnm_g), _ptr(lnm_b), _ptr(h1), _ptr(hn), B, N, cx, _stream()),
+             "am_cdm_decoder_point")
+
+
+def linear_skinny(x1, K1, x2, K2, W, bias, y, M, N, ldx1=None, ldx2=None, ldy=None):
+    _l.check(_l.load().am_linear_skinny(_ptr(x1), K1 if ldx1 is None else ldx1, K1, _ptr(x2), (K2 if ldx2 is None else ldx2), K2, _ptr(W),
+                                       _ptr(bias), _ptr(y), N if ldy is None else ldy, M, N, _stream()), "am_linear_skinny")
+    return y
+
+
+# ------------------------------------------------------------------ optional per-kernel CUDA-event profiler (bench.py)
+class KernelProfiler:
+    """Records a CUDA event pair around every op wrapper call on the launching (current torch) stream.
+    Used by bench.py's instrumented eager pass to attribute step time to kernels; never active on the timed path."""
+
+    def __init__(self):
+        self.records = []  # (name, start_event, end_event, flops)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for name, s, e, fl in self.records:
+            a = agg.setdefault(name, {"ms": 0.0, "launches": 0, "flops": 0.0})
+            a["ms"] += s.elapsed_time(e)
+            a["launches"] += 1
+            a["flops"] += fl
+        return agg
+
+
+PROFILER: Optional[KernelProfiler] = None
+
+
+def _flops_of(name, args, kwargs):
+    if name == "linear":
+        M, N, K = args[3], args[4], args[5]
+        return 2.0 * M * N * K
+    if name == "mha_fwd":
+        B, S, H, hd = args[3], args[4], args[5], args[6]
+        return 4.0 * B * H * S * S * hd
+    return 0.0
+
+
+def _wrap(name, fn):
+    def wrapped(*args, **kwargs):
+        prof = PROFILER
+        if prof is None:
+            return fn(*args, **kwargs)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        out = fn(*args, **kwargs)
+        e.record()
+        prof.records.append((name, s, e, _flops_of(name, args, kwargs)))
+        return out
+    wrapped.__name__ = fn.__name__
+    wrapped.__doc__ = fn.__doc__
+    return wrapped
+
+
+for _n in ("randn_", "p_sample_update", "ddim_update", "q_sample", "masked_mse", "add_i32", "linear", "layernorm", "mha_fwd",
+           "gather_time_token", "gather_rows", "furthestsampling", "knnquery", "pt_layer_fwd", "transition_down_fwd",
+           "cdm_encoder_partial", "cdm_encoder_combine", "cdm_decoder_point", "linear_skinny"):
+    globals()[_n] = _wrap(_n, globals()[_n])

@@ -1,0 +1,116 @@
+"""CDM (paper: ADM) — drop-in for /root/reference/models/cdm.py with arch='Perceiver'.
+
+Same class name / registry entry, constructor, `forward(x, timesteps, **kwargs)`, config keys
+(configs/model/cdm.yaml) and state_dict names; arithmetic in amb200.cdm_engine (CUDA).
+Out of scope: the ablation archs ContactMLP / ContactPointTrans(V2) and the frozen
+PointTransformerSeg scene model (§8 f3, "next") — selecting them raises NotImplementedError.
+"""
+import torch
+import torch.nn as nn
+
+from models.base import Model
+from models.functions import encode_text_clip, get_lang_feat_dim_type, load_and_freeze_clip_model
+from models.modules import CrossAttentionLayer, SelfAttentionBlock, TimestepEmbedder
+
+
+class ContactPerceiver(nn.Module):
+    """Parameter tree of cdm.py:88-153 (names identical)."""
+
+    def __init__(self, arch_cfg, contact_dim: int, point_feat_dim: int, text_feat_dim: int, time_emb_dim: int) -> None:
+        super().__init__()
+        self.point_pos_emb = arch_cfg.point_pos_emb
+        eq, ekv = arch_cfg.encoder_q_input_channels, arch_cfg.encoder_kv_input_channels
+        dq, dkv = arch_cfg.decoder_q_input_channels, arch_cfg.decoder_kv_input_channels
+        self.language_adapter = nn.Linear(text_feat_dim, eq, bias=True)
+        self.time_embedding_adapter = nn.Linear(time_emb_dim, eq, bias=True)
+        self.encoder_adapter = nn.Linear(contact_dim + point_feat_dim + (3 if self.point_pos_emb else 0), ekv, bias=True)
+        self.decoder_adapter = nn.Linear(ekv, dq, bias=True)
+        self.encoder_cross_attn = CrossAttentionLayer(arch_cfg.encoder_num_heads, eq, ekv, arch_cfg.encoder_widening_factor)
+        self.encoder_self_attn = SelfAttentionBlock(arch_cfg.encoder_self_attn_num_layers, arch_cfg.encoder_num_heads, eq,
+                                                    arch_cfg.encoder_widening_factor)
+        self.decoder_cross_attn = CrossAttentionLayer(arch_cfg.decoder_num_heads, dq, dkv, arch_cfg.decoder_widening_factor)
+
+
+@Model.register()
+class CDM(nn.Module):
+    def __init__(self, cfg, *args, **kwargs):
+        super().__init__()
+        self.device = kwargs["device"] if "device" in kwargs else "cpu"
+        self.contact_type = cfg.data_repr
+        self.contact_dim = cfg.input_feats
+        self.time_emb_dim = cfg.time_emb_dim
+        self.timestep_embedder = TimestepEmbedder(self.time_emb_dim, self.time_emb_dim, max_len=1000)
+
+        self.text_model_name = cfg.text_model.version
+        self.text_max_length = cfg.text_model.max_length
+        self.text_feat_dim, self.text_feat_type = get_lang_feat_dim_type(self.text_model_name)
+        if self.text_feat_type != "clip":
+            raise NotImplementedError("only CLIP text features are supported (every reference script uses ViT-B/32)")
+        self.text_model = load_and_freeze_clip_model(self.text_model_name)
+
+        if not cfg.scene_model.use_scene_model:
+            self.point_feat_dim = 0
+        elif cfg.scene_model.use_openscene:
+            self.point_feat_dim = cfg.scene_model.point_feat_dim  # features arrive precomputed in c_pc_feat
+        else:
+            raise NotImplementedError("frozen PointTransformerSeg scene model is a 'next' row (SURVEY §8 f3); "
+                                      "use scene_model.use_scene_model=False (H3D config) or precomputed point features")
+        self.arch = cfg.arch
+        if self.arch != "Perceiver":
+            raise NotImplementedError("afford-motion_b200 implements CDM arch='Perceiver' (the arch every reference script selects)")
+        self.arch_cfg = cfg.arch_perceiver
+        if not self.arch_cfg.point_pos_emb:
+            raise NotImplementedError("point_pos_emb=False is not used by any reference config")
+        self.contact_model = ContactPerceiver(self.arch_cfg, contact_dim=self.contact_dim, point_feat_dim=self.point_feat_dim,
+                                              text_feat_dim=self.text_feat_dim, time_emb_dim=self.time_emb_dim)
+        self.contact_layer = nn.Linear(self.arch_cfg.last_dim, self.contact_dim, bias=True)
+        self._engine = None
+        self._cond_cache = (None, None)
+
+    @property
+    def engine(self):
+        if self._engine is None:
+            from amb200.cdm_engine import CDMEngine
+            self._engine = CDMEngine(self)
+        return self._engine
+
+    def encode_condition(self, **kwargs):
+        self.engine.refresh()
+        xyz = kwargs["c_pc_xyz"]
+        pf = kwargs.get("c_pc_feat") if self.point_feat_dim > 0 else None
+
+        def tk(t):
+            return None if t is None else (t.data_ptr(), t._version, tuple(t.shape))
+        key = (tuple(kwargs["c_text"]), tk(xyz), tk(pf), self.engine._version)
+        if self._cond_cache[0] == key:
+            return self._cond_cache[1]
+        text = encode_text_clip(self.text_model, kwargs["c_text"], max_length=self.text_max_length, device=xyz.device).detach().float()
+        if pf is not None and self.point_feat_dim == 1 and pf.shape[-1] != 1:  # cdm.py:500-504 (openscene similarity feature)
+            pf = torch.einsum("bnd,bmd->bnm", pf, text.unsqueeze(1))
+        cond = self.engine.encode_condition(text, xyz, pf)
+        self._cond_cache = (key, cond)
+        return cond
+
+    def forward(self, x, timesteps, **kwargs):
+        """x [bs, num_points, contact_dim], timesteps int64 [bs] -> [bs, num_points, contact_dim]  (cdm.py:474-513)."""
+        if not x.is_cuda:
+            raise RuntimeError("afford-motion_b200: CDM runs on CUDA (sm_100a) only — there is no CPU fallback")
+        if torch.is_grad_enabled() and self.training:
+            raise NotImplementedError("afford-motion_b200 round 1: the CDM training (backward) path is not built yet; "
+                                      "call under torch.no_grad() / model.eval() for sampling")
+        cond = self.encode_condition(**kwargs)
+        t_dev = timesteps.to(device=x.device, dtype=torch.int32).contiguous()
+        return self.engine.forward(x.float().contiguous(), t_dev, 1, cond)
+
+    def sampler_begin(self, shape, model_kwargs, timestep_map):
+        """Device-resident sampling hook used by diffusion.gaussian_diffusion._fast_loop."""
+        cond = self.encode_condition(**model_kwargs)
+        eng = self.engine
+        tmap = torch.tensor(list(timestep_map), device=cond.xyz.device, dtype=torch.long)
+        table = eng.w["time_table"][tmap].contiguous()
+
+        class _Handle:
+            @staticmethod
+            def forward(x, t_dev, out):
+                return eng.forward(x, t_dev, 0, cond, out=out, time_table=table)
+        return _Handle()

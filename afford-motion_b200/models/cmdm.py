@@ -1,0 +1,125 @@
+"""CMDM (paper: AMDM) — drop-in for /root/reference/models/cmdm.py (arch='trans_enc').
+
+Same class name / registry entry, constructor `CMDM(cfg.model, device=...)`, `forward(x, timesteps, **kwargs)`,
+config keys (configs/model/cmdm.yaml) and state_dict names; the arithmetic runs in amb200.cmdm_engine (CUDA).
+`arch='trans_dec'` is out of scope (no reference script uses it).
+"""
+import torch
+import torch.nn as nn
+
+from models.base import Model
+from models.functions import encode_text_clip, get_lang_feat_dim_type, load_and_freeze_clip_model
+from models.modules import PositionalEncoding, SceneMapEncoder, TimestepEmbedder
+
+_REPR_DIM = {"smplx_no_hands": 69, "pos": 66, "pos_rot": 129, "contact_one_joints": 1, "contact_all_joints": 22,
+             "contact_cont_joints": 6, "contact_pelvis": 1, "h3d": 263}
+
+
+def compute_repr_dimesion(data_repr: str) -> int:
+    """utils/misc.py:4-22 (kept local: importing the reference's utils.misc instantiates an SMPL-X layer)."""
+    if data_repr not in _REPR_DIM:
+        raise ValueError(f"Unknown data representation: {data_repr}")
+    return _REPR_DIM[data_repr]
+
+
+@Model.register()
+class CMDM(nn.Module):
+    def __init__(self, cfg, *args, **kwargs):
+        super().__init__()
+        self.device = kwargs["device"] if "device" in kwargs else "cpu"
+        self.motion_type = cfg.data_repr
+        self.motion_dim = cfg.input_feats
+        self.latent_dim = cfg.latent_dim
+        self.mask_motion = cfg.mask_motion
+        self.arch = cfg.arch
+        if self.arch != "trans_enc":
+            raise NotImplementedError("afford-motion_b200 implements CMDM arch='trans_enc' (the only one the reference scripts use)")
+
+        self.time_emb_dim = cfg.time_emb_dim
+        self.timestep_embedder = TimestepEmbedder(self.latent_dim, self.time_emb_dim, max_len=1000)
+
+        self.contact_type = cfg.contact_model.contact_type
+        self.contact_dim = compute_repr_dimesion(self.contact_type)
+        self.planes = list(cfg.contact_model.planes)
+        self.contact_adapter = nn.Linear(self.planes[-1], self.latent_dim, bias=True)
+        self.contact_encoder = SceneMapEncoder(point_feat_dim=self.contact_dim, planes=self.planes,
+                                               blocks=list(cfg.contact_model.blocks), num_points=cfg.contact_model.num_points)
+
+        self.text_model_name = cfg.text_model.version
+        self.text_max_length = cfg.text_model.max_length
+        self.text_feat_dim, self.text_feat_type = get_lang_feat_dim_type(self.text_model_name)
+        if self.text_feat_type != "clip":
+            raise NotImplementedError("only CLIP text features are supported (every reference script uses ViT-B/32)")
+        self.text_model = load_and_freeze_clip_model(self.text_model_name)
+        self.language_adapter = nn.Linear(self.text_feat_dim, self.latent_dim, bias=True)
+
+        self.motion_adapter = nn.Linear(self.motion_dim, self.latent_dim, bias=True)
+        self.positional_encoder = PositionalEncoding(self.latent_dim, dropout=0.1, max_len=5000)
+        self.num_layers = list(cfg.num_layers)
+        # parameter container with torch's packed in_proj layout (checkpoint compatibility, cmdm.py:66-77)
+        self.self_attn_layer = nn.TransformerEncoder(
+            nn.TransformerEncoderLayer(d_model=self.latent_dim, nhead=cfg.num_heads, dim_feedforward=cfg.dim_feedforward,
+                                       dropout=cfg.dropout, activation="gelu", batch_first=True),
+            enable_nested_tensor=False, num_layers=sum(self.num_layers))
+        self.motion_layer = nn.Linear(self.latent_dim, self.motion_dim, bias=True)
+
+        self._engine = None
+        self._cond_cache = (None, None)
+
+    # ------------------------------------------------------------------ engine plumbing
+    @property
+    def engine(self):
+        if self._engine is None:
+            from amb200.cmdm_engine import CMDMEngine
+            self._engine = CMDMEngine(self)
+        return self._engine
+
+    def _cond_key(self, kwargs):
+        def tk(t):
+            return None if t is None else (t.data_ptr(), t._version, tuple(t.shape))
+        return (tuple(kwargs["c_text"]), tk(kwargs["c_pc_xyz"]), tk(kwargs["c_pc_contact"]), tk(kwargs.get("x_mask")),
+                tk(kwargs.get("c_text_mask")), tk(kwargs.get("c_text_erase")), tk(kwargs.get("c_pc_mask")), tk(kwargs.get("c_pc_erase")),
+                self.engine._version)
+
+    def encode_condition(self, T, **kwargs):
+        """Step-invariant conditioning (text token, contact tokens, key mask); cached while the inputs are unchanged."""
+        self.engine.refresh()
+        key = self._cond_key(kwargs)
+        if self._cond_cache[0] == key:
+            return self._cond_cache[1]
+        dev = kwargs["c_pc_xyz"].device
+        text = encode_text_clip(self.text_model, kwargs["c_text"], max_length=self.text_max_length, device=dev).detach().float()
+        B = kwargs["c_pc_xyz"].shape[0]
+        x_mask = kwargs.get("x_mask")
+        if x_mask is None:
+            x_mask = torch.zeros(B, T, dtype=torch.bool, device=dev)
+        cond = self.engine.encode_condition(text, kwargs["c_pc_xyz"], kwargs["c_pc_contact"], x_mask, T,
+                                            c_text_mask=kwargs.get("c_text_mask"), c_text_erase=kwargs.get("c_text_erase"),
+                                            c_pc_mask=kwargs.get("c_pc_mask"), c_pc_erase=kwargs.get("c_pc_erase"))
+        self._cond_cache = (key, cond)
+        return cond
+
+    def forward(self, x, timesteps, **kwargs):
+        """x [bs, seq_len, motion_dim], timesteps int64 [bs] -> [bs, seq_len, motion_dim]  (cmdm.py:118-196)."""
+        if not x.is_cuda:
+            raise RuntimeError("afford-motion_b200: CMDM runs on CUDA (sm_100a) only — there is no CPU fallback")
+        if torch.is_grad_enabled() and self.training:
+            raise NotImplementedError("afford-motion_b200 round 1: the CMDM training (backward) path is not built yet; "
+                                      "call under torch.no_grad() / model.eval() for sampling")
+        cond = self.encode_condition(x.shape[1], **kwargs)
+        t_dev = timesteps.to(device=x.device, dtype=torch.int32).contiguous()
+        return self.engine.forward(x.float().contiguous(), t_dev, 1, cond)
+
+    def sampler_begin(self, shape, model_kwargs, timestep_map):
+        """Device-resident sampling hook used by diffusion.gaussian_diffusion._fast_loop: conditioning encoded once,
+        time-token table re-indexed by the (respaced) timestep map so the device timestep indexes it directly."""
+        cond = self.encode_condition(shape[1], **model_kwargs)
+        eng = self.engine
+        tmap = torch.tensor(list(timestep_map), device=cond.static_tokens.device, dtype=torch.long)
+        table = eng.w["time_table"][tmap].contiguous()
+
+        class _Handle:
+            @staticmethod
+            def forward(x, t_dev, out):
+                return eng.forward(x, t_dev, 0, cond, out=out, time_table=table)
+        return _Handle()

@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json metric: denoise-steps/sec, CMDM 1000-step DDPM sampling, batch 32, T=196, D=263, N=8192.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--denoise-steps 1000]
+
+One bench "step" = ONE full sampling job of one batch: conditioning encode (text token + PointTransformer contact
+encoder, once) + `--denoise-steps` denoise steps (network evaluation + fused sampler update) + final sample.
+`value` = denoise-steps/s with inputs resident in HBM (whole job, all ranks); `e2e` = the same jobs through the public
+API (`diffusion.p_sample_loop(model, shape, model_kwargs=...)`) with HOST pinned inputs copied H2D and the sample
+copied D2H inside the timed region.  Weak scaling: every rank samples its own batch of 32 (no data-path collective).
+`--impl reference` times the CPU oracle port of the reference path (reference semantics: conditioning recomputed on
+every denoise step) on the host cores; each of its steps is ONE denoise step of the same batch.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (os.path.join(ROOT, "afford-motion_b200"), ROOT):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+B, T, DM, NPTS = 32, 196, 263, 8192
+METRIC = "denoise-steps/sec (CMDM T=196, N=8192, bs32)"
+# algorithmic work of one CMDM denoise step, per sample (conditioning cached)
+GFLOP_PER_SAMPLE_STEP = 8.066
+GEMM_GFLOP_PER_SAMPLE_STEP = 8.066 - 1.088  # everything except QK^T + PV
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured (MEASURED_PEAKS.json, sustained)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax = float(r[2])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_host_inputs(rank):
+    from amb200 import synth
+    seed = 2023 + rank
+    return dict(xyz=synth.scene_points(B, NPTS, seed=seed), contact=synth.contact_map(B, NPTS, seed=seed),
+                x_mask=synth.motion_mask(B, T, seed=seed, all_valid=True), text=synth.text_features(B, seed=seed),
+                texts=[f"prompt-{rank}-{i}" for i in range(B)])
+
+
+# ---------------------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_steps(nsteps, warmup, hoisted=False, threads=None):
+    """Oracle port of the reference path on the host cores: one denoise step of batch 32 per step.
+    as-written (hoisted=False): text/contact conditioning recomputed every step, like models/cmdm.py:133-149."""
+    from amb200 import synth
+    from amb200.config import cmdm_model_cfg
+    from models.base import Model
+    import models  # noqa: F401
+    from oracle import cmdm_ref, diffusion_ref as D
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    m = Model.get("CMDM")(cmdm_model_cfg(NPTS), device="cpu")
+    sd = synth.fill_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed=0)
+    m.load_state_dict(sd, strict=False)
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    inp = synth_host_inputs(0)
+    tab = D.make_tables(D.respaced(D.cosine_betas(1000), range(1000))[0])
+    x = synth.motion_noise(B, T, DM, seed=1)
+    cont = cmdm_ref.contact_tokens(sd, inp["xyz"], inp["contact"]) if hoisted else None
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + nsteps):
+            t = torch.full((B,), 999 - i, dtype=torch.long)
+            t0 = time.perf_counter()
+            x0 = cmdm_ref.cmdm_forward(sd, x, t, inp["text"], inp["xyz"], inp["contact"], inp["x_mask"], cont_emb=cont)
+            x = D.p_sample_step(tab, x0, x, t, torch.randn_like(x))
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    return sum(times), threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    total, threads = cpu_reference_steps(args.steps, args.warmup, hoisted=False)
+    v = args.steps / total
+    line = {"metric": METRIC, "value": v, "unit": "denoise-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": "CMDM 1000-step DDPM sampling, batch=32, T=196, D=263, N=8192 (configs[1])", "global_batch": B,
+                       "sample": "each step = 1 denoise step of the batch on the host CPU, conditioning recomputed per step "
+                                 "(reference semantics, models/cmdm.py:133-149)"},
+            "cpu_baseline": {"value": v, "unit": "denoise-steps/s", "cores": threads, "kind": "port",
+                             "sample": f"{args.steps} denoise steps at batch 32 (oracle port of the reference modules, torch CPU fp32 + C FPS/kNN)"},
+            "e2e": {"value": v, "unit": "denoise-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------- B200 arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--denoise-steps", type=int, default=1000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-steps", type=int, default=3)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from amb200 import lib, ops, synth
+    from amb200.config import cmdm_model_cfg, full_cfg
+    from models.base import create_model_and_diffusion
+    from models.functions import set_text_feature_provider
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback for the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib.check(lib.load().am_check_device(), "am_check_device")
+
+    nd = args.denoise_steps
+    model, diff = create_model_and_diffusion(full_cfg(cmdm_model_cfg(NPTS), steps=nd), device=dev)
+    sd = synth.fill_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed=0)
+    model.load_state_dict(sd, strict=False)
+    model.to(dev).eval()
+    diff.sample_offset = rank * B
+    host = synth_host_inputs(rank)
+    pinned = {k: host[k].pin_memory() for k in ("xyz", "contact", "x_mask", "text")}
+    text_dev = {}
+    set_text_feature_provider(lambda raw: text_dev["t"])
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)  # > 126 MB L2
+
+    def job_resident(kw):
+        flush.fill_(0.0)  # L2 flush between jobs (inside the region: ~0.1 ms per ~second-long job)
+        return diff.p_sample_loop(model, (B, T, DM), clip_denoised=False, model_kwargs=kw)
+
+    def job_e2e():
+        flush.fill_(0.0)
+        text_dev["t"] = pinned["text"].to(dev, non_blocking=True)
+        kw = dict(c_text=host["texts"], c_pc_xyz=pinned["xyz"].to(dev, non_blocking=True),
+                  c_pc_contact=pinned["contact"].to(dev, non_blocking=True), x_mask=pinned["x_mask"].to(dev, non_blocking=True))
+        out = diff.p_sample_loop(model, (B, T, DM), clip_denoised=False, model_kwargs=kw)
+        return out.to("cpu", non_blocking=False)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(k):
+            fn()
+        e.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    text_dev["t"] = host["text"].to(dev)
+    kw_res = dict(c_text=host["texts"], c_pc_xyz=host["xyz"].to(dev), c_pc_contact=host["contact"].to(dev), x_mask=host["x_mask"].to(dev))
+
+    def resident_once():
+        model._cond_cache = (None, None)  # every job re-encodes its conditioning (new batch semantics)
+        job_resident(kw_res)
+
+    for _ in range(args.warmup):
+        resident_once()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = lib.launch_count()
+    ms = timed(resident_once, args.steps)
+    launches = 0
+    # launches: per job = eager + graph replays (recorded by the loop) + conditioning encode (counted directly)
+    resident_once()
+    launches_per_job = diff.last_launches
+    ms_e2e = timed(job_e2e, args.steps)
+    clk = clocks.stop() if rank == 0 else None
+    del l0, launches
+
+    total_steps = args.steps * nd * world
+    value = total_steps / (ms / 1e3)
+    e2e_value = total_steps / (ms_e2e / 1e3)
+    h2d = sum(pinned[k].numel() * pinned[k].element_size() for k in pinned)
+    d2h = B * T * DM * 4
+
+    # ---- instrumented eager pass: per-kernel CUDA-event times for the roofline of the dominant kernel
+    roof, prof_out = None, None
+    if rank == 0:
+        cond = model.encode_condition(T, **kw_res)
+        x = torch.randn(B, T, DM, device=dev)
+        t_dev = torch.full((1,), nd // 2, device=dev, dtype=torch.int32)
+        x0 = torch.empty_like(x)
+        tab = diff._tables(dev)
+        for _ in range(2):
+            model.engine.forward(x, t_dev, 0, cond, out=x0)
+        ops.PROFILER = ops.KernelProfiler()
+        for _ in range(args.profile_steps):
+            flush.fill_(0.0)
+            model.engine.forward(x, t_dev, 0, cond, out=x0)
+            ops.p_sample_update(x0, x, x, None, tab["coef1"], tab["coef2"], tab["logvar"], t_dev, 0, seed=1)
+        agg = ops.PROFILER.summary()
+        ops.PROFILER = None
+        tot = sum(a["ms"] for a in agg.values())
+        prof_out = {k: {"ms_per_step": a["ms"] / args.profile_steps, "launches_per_step": a["launches"] / args.profile_steps,
+                        "share": a["ms"] / tot} for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
+        top = max(agg.items(), key=lambda kv: kv[1]["ms"])
+        hbm, tf, how = peaks()
+        if top[1]["flops"] > 0:
+            ach = top[1]["flops"] / (top[1]["ms"] / 1e3) / 1e12
+            roof = {"kernel": top[0], "bound": "tensor", "achieved": ach, "peak": tf, "unit": "TFLOP/s", "frac": ach / tf, "traffic": None,
+                    "peak_source": how, "avg_launch_ms": top[1]["ms"] / top[1]["launches"],
+                    "note": "achieved = algorithmic FLOPs (2MNK per GEMM launch / 4BHS^2d per attention launch) / CUDA-event time, "
+                            "instrumented eager pass outside the timed region"}
+
+    cpu_base = None
+    if rank == 0 and not args.no_cpu_baseline:
+        tot_s, threads = cpu_reference_steps(2, 1, hoisted=False)
+        tot_h, _ = cpu_reference_steps(3, 1, hoisted=True)
+        cpu_base = {"value": 2 / tot_s, "unit": "denoise-steps/s", "cores": threads, "kind": "port",
+                    "sample": "2 denoise steps at batch 32 after 1 warm-up, conditioning recomputed every step (reference semantics)",
+                    "hoisted_value": 3 / tot_h,
+                    "hoisted_sample": "3 denoise steps, conditioning computed once (what the B200 path does)"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "denoise-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "fp32", "data": "synthetic",
+                "config": {"workload": f"CMDM {nd}-step DDPM sampling, batch=32 per GPU, T=196, D=263, N=8192 (configs[1]); "
+                                       "bench step = one full sampling job incl. conditioning encode",
+                           "global_batch": B * world, "denoise_steps_per_job": nd, "parallelism": f"batch-sharded x{world}, no collective",
+                           "l2": "256 MB buffer written between jobs (L2 flush); per-step working set > 126 MB L2",
+                           "motions_per_s": value * B / nd, "tflops_algorithmic": value * B * GFLOP_PER_SAMPLE_STEP / 1e3},
+                "e2e": {"value": e2e_value, "unit": "denoise-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches_per_job * args.steps), "clocks": clk, "roofline": roof, "cpu_baseline": cpu_base,
+                "kernels": prof_out}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
