@@ -9,6 +9,7 @@ Design (B200-first, not a port of the reference's op-by-op graph):
   * every buffer is static per (B, T, G) so one denoise step is CUDA-graph capturable; the timestep lives on device.
 """
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, Optional
 
@@ -36,6 +37,9 @@ class CMDMEngine:
         self._version = None
         self.w: Dict[str, torch.Tensor] = {}
         self._ws = {}
+        # "tc": tcgen05 3-term bf16-split GEMMs (default); "simt": fp32 SIMT GEMMs (cross-check path)
+        self.gemm = os.environ.get("AMB200_GEMM", "tc")
+        assert self.gemm in ("tc", "simt")
 
     # ------------------------------------------------------------------ weights
     def refresh(self):
@@ -69,6 +73,14 @@ class CMDMEngine:
             w[p + "n1g"], w[p + "n1b"] = c(layer.norm1.weight), c(layer.norm1.bias)
             w[p + "n2g"], w[p + "n2b"] = c(layer.norm2.weight), c(layer.norm2.bias)
             w[p + "eps1"], w[p + "eps2"] = layer.norm1.eps, layer.norm2.eps
+        if self.gemm == "tc":  # bf16 (hi|lo) copies of the GEMM weights, K padded to 32
+            def sp(t):
+                return ops.split_bf16(t, t.shape[0], t.shape[1])
+            for name in ("motion_adapter", "motion_layer"):
+                w[name + ".w2"] = sp(w[name + ".w"])
+            for i in range(len(m.self_attn_layer.layers)):
+                for k in ("in_w", "out_w", "w1", "w2"):
+                    w[f"l{i}.{k}2"] = sp(w[f"l{i}.{k}"])
         self.w = w
         self.nlayers = len(m.self_attn_layer.layers)
         self.nhead = m.self_attn_layer.layers[0].self_attn.num_heads
@@ -122,6 +134,10 @@ class CMDMEngine:
                 "QKV": torch.empty(M, 3 * D, device=dev), "ATT": torch.empty(M, D, device=dev), "TMP": torch.empty(M, D, device=dev),
                 "Y1": torch.empty(M, D, device=dev), "FF": torch.empty(M, ff, device=dev), "cond_id": None,
             }
+            if self.gemm == "tc":
+                bf = lambda r, c: torch.zeros(r, c, dtype=torch.bfloat16, device=dev)
+                ws.update({"X0S": bf(M, 2 * D), "XSa": bf(M, 2 * D), "XSb": bf(M, 2 * D), "ATTS": bf(M, 2 * D), "Y1S": bf(M, 2 * D),
+                           "FFS": bf(M, 2 * ops.pad32(ff)), "xS": None})
             self._ws[key] = ws
         return ws
 
@@ -129,6 +145,11 @@ class CMDMEngine:
         """Copy the static tokens into the persistent token buffer (once per batch, not per step)."""
         if ws["cond_id"] is not cond:
             ws["X0"][:, 1:2 + cond.G, :].copy_(cond.static_tokens)
+            if self.gemm == "tc":
+                D = self.m.latent_dim
+                rows = cond.static_tokens.shape[0] * cond.static_tokens.shape[1]
+                st2 = ops.split_bf16(cond.static_tokens.view(rows, D), rows, D)
+                ws["X0S"].view(cond.B, -1, 2 * D)[:, 1:2 + cond.G, :].copy_(st2.view(cond.B, 1 + cond.G, 2 * D))
             ws["cond_id"] = cond
 
     # ------------------------------------------------------------------ one network evaluation
@@ -145,6 +166,8 @@ class CMDMEngine:
         ws = self.workspace(B, S, x.device)
         self.bind_condition(ws, cond)
         X0 = ws["X0"]
+        if self.gemm == "tc":
+            return self._forward_tc(x, t_dev, t_stride, cond, out, time_table, ws)
         ops.gather_time_token(X0, S, D, 0, w["time_table"] if time_table is None else time_table, t_dev, t_stride, B)
         # motion tokens + PE[2+G+j] -> rows 2+G.. of every sample   (cmdm.py:159-162)
         ops.linear(x, w["motion_adapter.w"], X0, B * T, D, Dm, bias=w["motion_adapter.b"], residual=w["pe"][2 + G:2 + G + T], ldr=D,
@@ -166,4 +189,43 @@ class CMDMEngine:
         if out is None:
             out = torch.empty(B, T, Dm, device=x.device)
         ops.linear(cur, w["motion_layer.w"], out, B * T, Dm, D, bias=w["motion_layer.b"], xmap=(T, S, 2 + G))
+        return out
+
+    def _forward_tc(self, x, t_dev, t_stride, cond, out, time_table, ws):
+        """Same network evaluation with every large GEMM on the tcgen05 path (3-term bf16 split, fp32 accumulate):
+        activations travel between GEMMs as bf16 (hi|lo) pairs written by the producing kernel's epilogue
+        (GEMM / LayerNorm / attention), fp32 copies are kept only where a residual or the attention kernel needs them."""
+        w, m = self.w, self.m
+        B, T, Dm = x.shape
+        G, D = cond.G, m.latent_dim
+        S = 2 + G + T
+        M = B * S
+        H = self.nhead
+        hd = D // H
+        X0, X0S = ws["X0"], ws["X0S"]
+        ops.gather_time_token(X0, S, D, 0, w["time_table"] if time_table is None else time_table, t_dev, t_stride, B, x2=X0S)
+        Kx = ops.pad32(Dm)
+        if ws["xS"] is None or ws["xS"].shape[0] != B * T:
+            ws["xS"] = torch.zeros(B * T, 2 * Kx, dtype=torch.bfloat16, device=x.device)
+        ops.split_bf16(x, B * T, Dm, out=ws["xS"])
+        ops.linear_tc(ws["xS"], w["motion_adapter.w2"], B * T, D, Kx, y=X0, y2=X0S, bias=w["motion_adapter.b"],
+                      residual=w["pe"][2 + G:2 + G + T], ldr=D, res_mod=T, ymap=(T, S, 2 + G), ldy=D, Np2=D)
+        cur, curS = X0.view(M, D), X0S
+        ffp = ops.pad32(self.ff)
+        for i in range(self.nlayers):
+            p = f"l{i}."
+            last = i == self.nlayers - 1
+            nxt, nxtS = (ws["Xa"], ws["XSa"]) if i % 2 == 0 else (ws["Xb"], ws["XSb"])
+            ops.linear_tc(curS, w[p + "in_w2"], M, 3 * D, D, y=ws["QKV"], bias=w[p + "in_b"])
+            ops.mha_fwd(ws["QKV"], None, cond.key_pad, B, S, H, hd, 1.0 / math.sqrt(hd), out2=ws["ATTS"])
+            ops.linear_tc(ws["ATTS"], w[p + "out_w2"], M, D, D, y=ws["TMP"], bias=w[p + "out_b"], residual=cur)
+            ops.layernorm(ws["TMP"], w[p + "n1g"], w[p + "n1b"], ws["Y1"], M, D, eps=w[p + "eps1"], y2=ws["Y1S"])
+            ops.linear_tc(ws["Y1S"], w[p + "w12"], M, self.ff, D, y2=ws["FFS"], bias=w[p + "b1"], act="gelu", Np2=ffp)
+            ops.linear_tc(ws["FFS"], w[p + "w22"], M, D, ffp, y=ws["TMP"], bias=w[p + "b2"], residual=ws["Y1"])
+            ops.layernorm(ws["TMP"], w[p + "n2g"], w[p + "n2b"], None if last else nxt, M, D, eps=w[p + "eps2"], y2=nxtS)
+            cur, curS = nxt, nxtS
+        if out is None:
+            out = torch.empty(B, T, Dm, device=x.device)
+        # motion_layer over all tokens; only rows s >= 2+G are written (skip map) -> out [B*T, Dm]
+        ops.linear_tc(curS, w["motion_layer.w2"], M, Dm, D, y=out, bias=w["motion_layer.b"], ymap=(S, T, -(2 + G)), ldy=Dm)
         return out

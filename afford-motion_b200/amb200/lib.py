@@ -28,9 +28,9 @@ _SIGS = {
     "am_masked_mse": (c_int, [P, P, P, P, I, I, I, P]),
     "am_add_i32": (c_int, [P, c_int32, I, P]),
     "am_linear_f32": (c_int, [P, I, P, I, P, I, I, I, I, P, I, P, I, I, I, I, I, I, I, I, P]),
-    "am_layernorm": (c_int, [P, I, P, I, P, P, P, I, I, I, c_float, P]),
-    "am_mha_fwd": (c_int, [P, P, P, I, I, I, I, c_float, P]),
-    "am_gather_time_token": (c_int, [P, I, I, I, P, P, I, I, P]),
+    "am_layernorm": (c_int, [P, I, P, I, P, P, P, I, I, I, c_float, P, I, P]),
+    "am_mha_fwd": (c_int, [P, P, P, I, I, I, I, c_float, P, P]),
+    "am_gather_time_token": (c_int, [P, I, I, I, P, P, I, I, P, P]),
     "am_gather_rows": (c_int, [P, P, P, I, I, P]),
     "am_furthestsampling": (c_int, [I, I, P, P, P, P, P, P]),
     "am_knnquery": (c_int, [I, I, I, P, P, P, P, P, P, P]),
@@ -40,6 +40,8 @@ _SIGS = {
     "am_cdm_encoder_combine": (c_int, [P, P, I, I, P]),
     "am_cdm_decoder_point": (c_int, [P, P, P, P, P, P, P, I, P, P, P, P, P, P, I, I, I, P]),
     "am_linear_skinny": (c_int, [P, I, I, P, I, I, P, P, P, I, I, I, P]),
+    "am_split_bf16": (c_int, [P, I, P, I, I, I, P]),
+    "am_linear_tc": (c_int, [P, P, I, I, I, P, I, P, I, I, P, I, I, I, I, P, I, P]),
 }
 
 _lib = None

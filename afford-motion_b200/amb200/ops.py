@@ -86,21 +86,23 @@ def linear(x, w, y, M, N, K, bias=None, act=None, residual=None, ldx=None, ldw=N
     return y
 
 
-def layernorm(x, gamma, beta, y, M, D, residual=None, eps=1e-5, ldx=None, ldy=None, ldr=None):
-    _chk_cuda(x, y)
+def layernorm(x, gamma, beta, y, M, D, residual=None, eps=1e-5, ldx=None, ldy=None, ldr=None, y2=None):
+    _chk_cuda(x)
     _l.check(_l.load().am_layernorm(_ptr(x), D if ldx is None else ldx, _ptr(residual), D if ldr is None else ldr, _ptr(gamma),
-                                   _ptr(beta), _ptr(y), D if ldy is None else ldy, M, D, eps, _stream()), "am_layernorm")
+                                   _ptr(beta), _ptr(y), D if ldy is None else ldy, M, D, eps, _ptr(y2), pad32(D) if y2 is not None else 0,
+                                   _stream()), "am_layernorm")
     return y
 
 
-def mha_fwd(qkv, out, key_pad_u8, B, S, H, hd, scale):
-    _chk_cuda(qkv, out)
-    _l.check(_l.load().am_mha_fwd(_ptr(qkv), _ptr(out), _ptr(key_pad_u8), B, S, H, hd, float(scale), _stream()), "am_mha_fwd")
+def mha_fwd(qkv, out, key_pad_u8, B, S, H, hd, scale, out2=None):
+    _chk_cuda(qkv)
+    _l.check(_l.load().am_mha_fwd(_ptr(qkv), _ptr(out), _ptr(key_pad_u8), B, S, H, hd, float(scale), _ptr(out2), _stream()), "am_mha_fwd")
     return out
 
 
-def gather_time_token(X, S, D, row, table, t, t_stride, B):
-    _l.check(_l.load().am_gather_time_token(_ptr(X), S, D, row, _ptr(table), _ptr(t), t_stride, B, _stream()), "am_gather_time_token")
+def gather_time_token(X, S, D, row, table, t, t_stride, B, x2=None):
+    _l.check(_l.load().am_gather_time_token(_ptr(X), S, D, row, _ptr(table), _ptr(t), t_stride, B, _ptr(x2), _stream()),
+             "am_gather_time_token")
 
 
 def gather_rows(src, idx, dst, m, c):
@@ -164,6 +166,32 @@ def linear_skinny(x1, K1, x2, K2, W, bias, y, M, N, ldx1=None, ldx2=None, ldy=No
     return y
 
 
+def pad32(k: int) -> int:
+    return (k + 31) // 32 * 32
+
+
+def split_bf16(x, M, K, out=None, ldx=None):
+    """fp32 [M,K] -> bf16 (hi|lo) [M, 2*Kp] operand of am_linear_tc."""
+    _chk_cuda(x)
+    Kp = pad32(K)
+    if out is None:
+        out = torch.empty(M, 2 * Kp, dtype=torch.bfloat16, device=x.device)
+    _l.check(_l.load().am_split_bf16(_ptr(x), K if ldx is None else ldx, _ptr(out), Kp, M, K, _stream()), "am_split_bf16")
+    return out
+
+
+def linear_tc(a2, w2, M, N, Kp, y=None, y2=None, bias=None, act=None, residual=None, ldr=0, res_mod=0, ldy=None, ymap=(0, 0, 0), Np2=0):
+    """tcgen05 GEMM on split-bf16 operands (see am_linear_tc)."""
+    _chk_cuda(a2, w2)
+    if residual is not None and ldr == 0:
+        ldr = N
+    if y2 is not None and Np2 == 0:
+        Np2 = pad32(N)
+    _l.check(_l.load().am_linear_tc(_ptr(a2), _ptr(w2), M, N, Kp, _ptr(bias), ACT[act], _ptr(residual), ldr, res_mod, _ptr(y),
+                                   N if ldy is None else ldy, ymap[0], ymap[1], ymap[2], _ptr(y2), Np2, _stream()), "am_linear_tc")
+    return y if y is not None else y2
+
+
 # ------------------------------------------------------------------ optional per-kernel CUDA-event profiler (bench.py)
 class KernelProfiler:
     """Records a CUDA event pair around every op wrapper call on the launching (current torch) stream.
@@ -190,6 +218,8 @@ def _flops_of(name, args, kwargs):
     if name == "linear":
         M, N, K = args[3], args[4], args[5]
         return 2.0 * M * N * K
+    if name == "linear_tc":
+        return 2.0 * args[2] * args[3] * args[4]
     if name == "mha_fwd":
         B, S, H, hd = args[3], args[4], args[5], args[6]
         return 4.0 * B * H * S * S * hd
@@ -214,5 +244,5 @@ def _wrap(name, fn):
 
 for _n in ("randn_", "p_sample_update", "ddim_update", "q_sample", "masked_mse", "add_i32", "linear", "layernorm", "mha_fwd",
            "gather_time_token", "gather_rows", "furthestsampling", "knnquery", "pt_layer_fwd", "transition_down_fwd",
-           "cdm_encoder_partial", "cdm_encoder_combine", "cdm_decoder_point", "linear_skinny"):
+           "cdm_encoder_partial", "cdm_encoder_combine", "cdm_decoder_point", "linear_skinny", "split_bf16", "linear_tc"):
     globals()[_n] = _wrap(_n, globals()[_n])

@@ -4,6 +4,7 @@
 // (S <= 352 keeps K^T + V + P inside the 227 KB carve-out); each warp processes 4 queries at a time:
 // scores with lanes over keys, softmax in registers, P through smem, PV with lanes over head dims.
 #include <math_constants.h>
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace {
@@ -15,7 +16,8 @@ constexpr int QTILE = 128;   // queries per CTA
 constexpr int MAXJ = 11;     // ceil(352/32)
 
 __global__ void __launch_bounds__(ATT_WARPS * 32, 1)
-mha_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out, const uint8_t* __restrict__ key_pad, int S, int H, float scale) {
+mha_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out, const uint8_t* __restrict__ key_pad, int S, int H, float scale,
+               __nv_bfloat16* __restrict__ out2) {
     extern __shared__ __align__(16) float smem[];
     const int SP = ((S + 31) / 32) * 32 + 1;
     float* Kt = smem;                         // [HD][SP]
@@ -115,7 +117,18 @@ mha_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out, const uin
 #pragma unroll
         for (int qi = 0; qi < QW; ++qi) {
             int q = qb + qi;
-            if (q < S) *reinterpret_cast<float2*>(out + ((int64_t)b * S + q) * (H * HD) + h * HD + 2 * lane) = make_float2(o[qi][0], o[qi][1]);
+            if (q < S) {
+                int64_t row = (int64_t)b * S + q;
+                if (out) *reinterpret_cast<float2*>(out + row * (H * HD) + h * HD + 2 * lane) = make_float2(o[qi][0], o[qi][1]);
+                if (out2) {  // bf16 (hi | lo) operand of the out_proj tcgen05 GEMM; row stride 2*H*HD
+                    __nv_bfloat16 h0 = __float2bfloat16_rn(o[qi][0]), h1 = __float2bfloat16_rn(o[qi][1]);
+                    __nv_bfloat162 hi2; hi2.x = h0; hi2.y = h1;
+                    __nv_bfloat162 lo2; lo2.x = __float2bfloat16_rn(o[qi][0] - __bfloat162float(h0)); lo2.y = __float2bfloat16_rn(o[qi][1] - __bfloat162float(h1));
+                    __nv_bfloat16* base2 = out2 + row * (2 * H * HD) + h * HD + 2 * lane;
+                    *reinterpret_cast<__nv_bfloat162*>(base2) = hi2;
+                    *reinterpret_cast<__nv_bfloat162*>(base2 + H * HD) = lo2;
+                }
+            }
         }
         __syncwarp();
     }
@@ -123,8 +136,9 @@ mha_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out, const uin
 
 }  // namespace
 
-extern "C" int am_mha_fwd(const float* qkv, float* out, const uint8_t* key_pad, int B, int S, int H, int hd, float scale, am_stream_t stream) {
-    AM_REQUIRE(qkv && out && B > 0 && S > 0 && H > 0, AM_EINVAL, "am_mha_fwd: bad args");
+extern "C" int am_mha_fwd(const float* qkv, float* out, const uint8_t* key_pad, int B, int S, int H, int hd, float scale, void* out2,
+                          am_stream_t stream) {
+    AM_REQUIRE(qkv && (out || out2) && B > 0 && S > 0 && H > 0, AM_EINVAL, "am_mha_fwd: bad args");
     AM_REQUIRE(hd == HD, AM_EINVAL, "am_mha_fwd: head dim must be 64");
     AM_REQUIRE(S <= 32 * MAXJ, AM_EINVAL, "am_mha_fwd: S must be <= 352");
     AM_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15u) == 0 && (reinterpret_cast<uintptr_t>(out) & 7u) == 0, AM_EALIGN, "am_mha_fwd: alignment");
@@ -140,7 +154,7 @@ extern "C" int am_mha_fwd(const float* qkv, float* out, const uint8_t* key_pad, 
     }
     AM_REQUIRE(smem <= 227 * 1024, AM_EINVAL, "am_mha_fwd: sequence too long for the shared-memory staging");
     dim3 grid(cdiv(S, QTILE), H, B);
-    mha_fwd_kernel<<<grid, ATT_WARPS * 32, smem, as_stream(stream)>>>(qkv, out, key_pad, S, H, scale);
+    mha_fwd_kernel<<<grid, ATT_WARPS * 32, smem, as_stream(stream)>>>(qkv, out, key_pad, S, H, scale, reinterpret_cast<__nv_bfloat16*>(out2));
     AM_LAUNCH_CHECK("mha_fwd");
     return AM_OK;
 }

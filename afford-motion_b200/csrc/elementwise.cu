@@ -1,6 +1,7 @@
 // Diffusion sampler / loss elementwise kernels: HBM-bound, 128-bit vectorised where alignment allows,
 // timestep read from device memory so a captured CUDA graph can be replayed for every step.
 // Reference math: diffusion/gaussian_diffusion.py (see include/amb200.h for line cites).
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace {
@@ -131,12 +132,20 @@ __global__ void add_i32_kernel(int32_t* dst, int32_t delta, int n) {
 }
 
 __global__ void gather_time_token_kernel(float* __restrict__ X, int S, int D, int row, const float* __restrict__ table,
-                                         const int32_t* __restrict__ t, int t_stride) {
+                                         const int32_t* __restrict__ t, int t_stride, __nv_bfloat16* __restrict__ X2) {
     int b = blockIdx.x;
     int tb = t[b * t_stride];
     const float* src = table + (int64_t)tb * D;
     float* dst = X + ((int64_t)b * S + row) * D;
-    for (int d = threadIdx.x; d < D; d += blockDim.x) dst[d] = src[d];
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float v = src[d];
+        dst[d] = v;
+        if (X2) {  // bf16 (hi | lo) copy of the token buffer, row stride 2*D
+            __nv_bfloat16 h = __float2bfloat16_rn(v);
+            X2[((int64_t)b * S + row) * 2 * D + d] = h;
+            X2[((int64_t)b * S + row) * 2 * D + D + d] = __float2bfloat16_rn(v - __bfloat162float(h));
+        }
+    }
 }
 
 __global__ void gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, float* __restrict__ dst, int m, int c) {
@@ -213,9 +222,9 @@ extern "C" int am_add_i32(int32_t* dst, int32_t delta, int n, am_stream_t stream
 }
 
 extern "C" int am_gather_time_token(float* X, int S, int D, int row, const float* table, const int32_t* t, int t_stride, int B,
-                                    am_stream_t stream) {
+                                    void* X2, am_stream_t stream) {
     AM_REQUIRE(X && table && t && B > 0 && S > 0 && D > 0 && row >= 0 && row < S, AM_EINVAL, "am_gather_time_token: bad args");
-    gather_time_token_kernel<<<B, 128, 0, as_stream(stream)>>>(X, S, D, row, table, t, t_stride);
+    gather_time_token_kernel<<<B, 128, 0, as_stream(stream)>>>(X, S, D, row, table, t, t_stride, reinterpret_cast<__nv_bfloat16*>(X2));
     AM_LAUNCH_CHECK("gather_time_token");
     return AM_OK;
 }

@@ -1,0 +1,342 @@
+// tcgen05 tensor-core GEMM with fp32-equivalent accuracy (3-term bf16 split), sm_100a only.
+//
+//   Y[M,N] = act( A[M,K] W[N,K]^T + bias ) (+ residual)
+//   A = A_hi + A_lo, W = W_hi + W_lo (bf16 pairs, 16 significant bits each)  ->
+//   A W^T ~= A_lo W_hi^T + A_hi W_lo^T + A_hi W_hi^T     (fp32 accumulation in TMEM; dropped term ~2^-16 relative)
+//
+// Why not plain bf16 / tf32: the parity budget is 1e-3 max-abs vs the fp32 reference; one bf16 pass measures
+// 1.9e-2 on CMDM and kind::tf32 truncates to 10 mantissa bits (~2.4e-3).  3 bf16 MMAs per product
+// cost 3/2.25 PF = 1.33 us/TFLOP — still 10x the fp32 SIMT pipe.
+//
+// Kernel shape (one 128x128 output tile per CTA, 2 CTAs co-resident per SM so one CTA's epilogue overlaps the
+// other's main loop):
+//   warp 0      : TMA producer  — per K-block of 32 loads the FOUR 128x32 sub-tiles {A_hi, A_lo, W_hi, W_lo}
+//                 (SWIZZLE_64B, 8 KB each) exactly once into a 3-stage mbarrier ring (each sub-tile feeds 2 MMAs)
+//   warp 1      : MMA issuer    — one thread issues 6 x tcgen05.mma (M128 N128 K16, kind::f16 bf16->f32) per stage,
+//                 tcgen05.commit releases the stage / signals the epilogue
+//   warp 2      : TMEM allocator (128 columns)
+//   warps 4..7  : epilogue      — tcgen05.ld 32x32b.x32 (one accumulator row per thread), bias / activation /
+//                 residual / token row map, fp32 store and/or bf16 (hi|lo) split store for the next GEMM
+// Operand layout in HBM: A2 [M, 2*Kp] bf16 = (hi | lo), W2 [N, 2*Kp] bf16 = (hi | lo), Kp % 32 == 0, zero padded.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 32;
+constexpr int STAGES = 3;
+constexpr int SUB_BYTES = BM * BK * 2;         // 8 KB : one 128x32 bf16 sub-tile
+constexpr int STAGE_BYTES = 4 * SUB_BYTES;     // A_hi, A_lo, W_hi, W_lo
+constexpr int TMEM_COLS = 128;
+constexpr int TC_THREADS = 256;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct TcParams {
+    int M, N, Kp;
+    const float* bias; int act;
+    const float* residual; int ldr; int res_mod;
+    float* Y; int ldy; int yin_g, yout_g, y_off;
+    __nv_bfloat16* Y2; int Np2;
+    int vecY;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded spin: a protocol bug traps (reported as a launch failure) instead of hanging the GPU box
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > 200000000u) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* holder, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(holder)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t r[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major operand tile in shared memory, SWIZZLE_64B: rows of 32 bf16 (64 B), 8-row groups 512 B apart.
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout [61,64))
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;                 // LBO (ignored for swizzled K-major; CUTLASS writes 1)
+    d |= (uint64_t)(512 >> 4) << 32;        // SBO = 8 rows * 64 B
+    d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+    d |= (uint64_t)4 << 61;                 // LayoutType::SWIZZLE_64B
+    return d;
+}
+// cute::UMMA::InstrDescriptor: c_format F32 [4,6)=1 | a_format BF16 [7,10)=1 | b_format BF16 [10,13)=1 | K-major A/B
+// (bits 15,16 = 0) | N>>3 [17,23) | M>>4 [24,29)
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ int64_t map_row_tc(int m, int gin, int gout, int off, bool& valid) {
+    valid = true;
+    if (gin <= 0) return m;
+    int r = off + (m % gin);
+    valid = r >= 0 && r < gout;
+    return (int64_t)(m / gin) * gout + r;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int nkb = p.Kp / BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc(tmem_holder, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                int s = kb % STAGES;
+                uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                uint8_t* st = smem + s * STAGE_BYTES;
+                mbar_expect_tx(&full[s], STAGE_BYTES);
+                tma_load_2d(st + 0 * SUB_BYTES, &tmA, &full[s], kb * BK, m0);          // A_hi
+                tma_load_2d(st + 1 * SUB_BYTES, &tmA, &full[s], p.Kp + kb * BK, m0);   // A_lo
+                tma_load_2d(st + 2 * SUB_BYTES, &tmB, &full[s], kb * BK, n0);          // W_hi
+                tma_load_2d(st + 3 * SUB_BYTES, &tmB, &full[s], p.Kp + kb * BK, n0);   // W_lo
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (single thread) =====================
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                int s = kb % STAGES;
+                uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+                uint64_t a_hi = make_desc_sw64(base), a_lo = make_desc_sw64(base + SUB_BYTES);
+                uint64_t w_hi = make_desc_sw64(base + 2 * SUB_BYTES), w_lo = make_desc_sw64(base + 3 * SUB_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {  // K=16 per MMA -> +32 B inside the 64 B swizzle row (encoded +2)
+                    uint64_t ko = (uint64_t)(k * 2);
+                    umma_bf16(tmem_base, a_lo + ko, w_hi + ko, IDESC, (kb | k) ? 1u : 0u);
+                    umma_bf16(tmem_base, a_hi + ko, w_lo + ko, IDESC, 1u);
+                    umma_bf16(tmem_base, a_hi + ko, w_hi + ko, IDESC, 1u);
+                }
+                umma_commit(&empty[s]);               // stage free once these MMAs retire
+                if (kb == nkb - 1) umma_commit(tmem_full);
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: one accumulator row per thread =====================
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int m = m0 + r;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        bool row_ok = m < p.M, map_ok = true;
+        int64_t yrow = row_ok ? map_row_tc(m, p.yin_g, p.yout_g, p.y_off, map_ok) : 0;
+        row_ok = row_ok && map_ok;
+        const float* rrow = nullptr;
+        if (p.residual && row_ok) rrow = p.residual + (p.res_mod > 0 ? (int64_t)(m % p.res_mod) : yrow) * p.ldr;
+        const int act = p.act & 15;
+        const bool after = (p.act & AM_ACT_AFTER_RES) != 0;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+            if (!row_ok) continue;
+            const int nb = n0 + c * 32;
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                int n = nb + j;
+                float x = __uint_as_float(v[j]);
+                if (n < p.N) {
+                    if (p.bias) x += p.bias[n];
+                    if (after) { if (rrow) x += rrow[n]; x = apply_act(x, act); }
+                    else { x = apply_act(x, act); if (rrow) x += rrow[n]; }
+                } else x = 0.f;
+                f[j] = x;
+            }
+            if (p.Y) {
+                float* dst = p.Y + yrow * p.ldy + nb;
+                if (p.vecY && nb + 31 < p.N) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (nb + j < p.N) dst[j] = f[j];
+                }
+            }
+            if (p.Y2 && nb < p.Np2) {  // Np2 % 32 == 0: a chunk is either fully inside the padded width or skipped
+                __nv_bfloat16* hi = p.Y2 + yrow * (2 * (int64_t)p.Np2) + nb;
+                __nv_bfloat16* lo = hi + p.Np2;
+                uint32_t ph[16], pl[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    __nv_bfloat16 h0 = __float2bfloat16_rn(f[j]), h1 = __float2bfloat16_rn(f[j + 1]);
+                    __nv_bfloat16 l0 = __float2bfloat16_rn(f[j] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(f[j + 1] - __bfloat162float(h1));
+                    ph[j / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                    pl[j / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    *reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(hi) + j) = make_uint4(ph[j], ph[j + 1], ph[j + 2], ph[j + 3]);
+                    *reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(lo) + j) = make_uint4(pl[j], pl[j + 1], pl[j + 2], pl[j + 3]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// fp32 [M,K] -> bf16 (hi | lo) [M, 2*Kp], zero padded to Kp
+__global__ void split_bf16_kernel(const float* __restrict__ X, int ldx, __nv_bfloat16* __restrict__ X2, int Kp, int M, int K) {
+    int64_t total = (int64_t)M * Kp;
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        int m = (int)(g / Kp), k = (int)(g - (int64_t)m * Kp);
+        float v = k < K ? X[(int64_t)m * ldx + k] : 0.f;
+        __nv_bfloat16 h = __float2bfloat16_rn(v);
+        __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+        X2[(int64_t)m * 2 * Kp + k] = h;
+        X2[(int64_t)m * 2 * Kp + Kp + k] = l;
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D bf16 tensor [rows, cols] row-major, box = 32 cols x 128 rows, SWIZZLE_64B, OOB -> zeros
+bool make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {cols * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+extern "C" int am_split_bf16(const float* X, int ldx, void* X2, int Kp, int M, int K, am_stream_t stream) {
+    AM_REQUIRE(X && X2 && M > 0 && K > 0 && Kp >= K && Kp % BK == 0 && ldx >= K, AM_EINVAL, "am_split_bf16: bad args (Kp % 32 == 0)");
+    int64_t total = (int64_t)M * Kp;
+    int64_t blocks = (total + 255) / 256;
+    int grid = (int)(blocks < (int64_t)AM_NUM_SMS * 8 ? blocks : (int64_t)AM_NUM_SMS * 8);
+    split_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>(X, ldx, reinterpret_cast<__nv_bfloat16*>(X2), Kp, M, K);
+    AM_LAUNCH_CHECK("split_bf16");
+    return AM_OK;
+}
+
+extern "C" int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp, const float* bias, int act, const float* residual, int ldr,
+                            int res_mod, float* Y, int ldy, int yin_g, int yout_g, int y_off, void* Y2, int Np2, am_stream_t stream) {
+    AM_REQUIRE(A2 && W2 && (Y || Y2), AM_EINVAL, "am_linear_tc: null pointer");
+    AM_REQUIRE(M > 0 && N > 0 && Kp > 0 && Kp % BK == 0, AM_EINVAL, "am_linear_tc: Kp must be a positive multiple of 32");
+    AM_REQUIRE((act & 15) <= 3 && (act & ~31) == 0, AM_EINVAL, "am_linear_tc: bad activation");
+    AM_REQUIRE(!Y || ldy >= N, AM_EINVAL, "am_linear_tc: bad ldy");
+    AM_REQUIRE(!Y2 || (Np2 >= N && Np2 % 32 == 0), AM_EINVAL, "am_linear_tc: Np2 must be a multiple of 32 and >= N");
+    AM_REQUIRE(!residual || ldr >= N, AM_EINVAL, "am_linear_tc: bad residual stride");
+    AM_REQUIRE((reinterpret_cast<uintptr_t>(A2) & 15u) == 0 && (reinterpret_cast<uintptr_t>(W2) & 15u) == 0 &&
+               (!Y2 || (reinterpret_cast<uintptr_t>(Y2) & 15u) == 0), AM_EALIGN, "am_linear_tc: operands must be 16-byte aligned");
+    CUtensorMap tmA, tmB;
+    AM_REQUIRE(make_map(&tmA, A2, (uint64_t)M, (uint64_t)2 * Kp), AM_ELAUNCH, "am_linear_tc: cuTensorMapEncodeTiled(A) failed");
+    AM_REQUIRE(make_map(&tmB, W2, (uint64_t)N, (uint64_t)2 * Kp), AM_ELAUNCH, "am_linear_tc: cuTensorMapEncodeTiled(W) failed");
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
+            am_set_error_("am_linear_tc: shared memory opt-in failed");
+            return AM_ELAUNCH;
+        }
+        attr = true;
+    }
+    TcParams p{M, N, Kp, bias, act, residual, ldr, res_mod, Y, ldy, yin_g, yout_g, y_off, reinterpret_cast<__nv_bfloat16*>(Y2), Np2, 0};
+    p.vecY = Y && (reinterpret_cast<uintptr_t>(Y) & 15u) == 0 && (ldy % 4 == 0);
+    dim3 grid(cdiv(N, BN), cdiv(M, BM));
+    gemm_tc_kernel<<<grid, TC_THREADS, SMEM_BYTES, as_stream(stream)>>>(tmA, tmB, p);
+    AM_LAUNCH_CHECK("linear_tc");
+    return AM_OK;
+}

@@ -1,5 +1,6 @@
 // Y = LayerNorm(X (+R)) * gamma + beta — one warp per row, row cached in registers (D <= 1024),
 // two-pass mean / variance in fp32 (matches torch.nn.LayerNorm, eps inside the sqrt).
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace {
@@ -7,7 +8,8 @@ namespace {
 template <int MAXV>  // MAXV = ceil(D/32) upper bound
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ R, int ldr,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                        float* __restrict__ Y, int ldy, int M, int D, float eps) {
+                                                        float* __restrict__ Y, int ldy, int M, int D, float eps,
+                                                        __nv_bfloat16* __restrict__ Y2, int Np2) {
     int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= M) return;
     int lane = threadIdx.x & 31;
@@ -31,24 +33,37 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
         q += t * t;
     }
     float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
-    float* y = Y + (int64_t)row * ldy;
+    float* y = Y ? Y + (int64_t)row * ldy : nullptr;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
         int d = lane + i * 32;
-        if (d < D) y[d] = (v[i] - mean) * rstd * gamma[d] + beta[d];
+        if (d < D) {
+            float o = (v[i] - mean) * rstd * gamma[d] + beta[d];
+            if (Y) y[d] = o;
+            if (Y2) {  // bf16 (hi | lo) operand of the next tcgen05 GEMM
+                __nv_bfloat16 h = __float2bfloat16_rn(o);
+                Y2[(int64_t)row * 2 * Np2 + d] = h;
+                Y2[(int64_t)row * 2 * Np2 + Np2 + d] = __float2bfloat16_rn(o - __bfloat162float(h));
+            }
+        } else if (Y2 && d < Np2) {
+            Y2[(int64_t)row * 2 * Np2 + d] = __float2bfloat16_rn(0.f);
+            Y2[(int64_t)row * 2 * Np2 + Np2 + d] = __float2bfloat16_rn(0.f);
+        }
     }
 }
 
 }  // namespace
 
 extern "C" int am_layernorm(const float* X, int ldx, const float* R, int ldr, const float* gamma, const float* beta, float* Y, int ldy,
-                            int M, int D, float eps, am_stream_t stream) {
-    AM_REQUIRE(X && gamma && beta && Y && M > 0 && D > 0 && D <= 1024, AM_EINVAL, "am_layernorm: bad args (D <= 1024)");
-    AM_REQUIRE(ldx >= D && ldy >= D && (!R || ldr >= D), AM_EINVAL, "am_layernorm: bad strides");
+                            int M, int D, float eps, void* Y2, int Np2, am_stream_t stream) {
+    AM_REQUIRE(X && gamma && beta && (Y || Y2) && M > 0 && D > 0 && D <= 1024, AM_EINVAL, "am_layernorm: bad args (D <= 1024)");
+    AM_REQUIRE(ldx >= D && (!Y || ldy >= D) && (!R || ldr >= D), AM_EINVAL, "am_layernorm: bad strides");
+    AM_REQUIRE(!Y2 || (Np2 >= D && Np2 % 32 == 0 && Np2 <= 1024), AM_EINVAL, "am_layernorm: bad Np2");
+    __nv_bfloat16* y2 = reinterpret_cast<__nv_bfloat16*>(Y2);
     int grid = cdiv(M, 8);
-    if (D <= 256) layernorm_kernel<8><<<grid, 256, 0, as_stream(stream)>>>(X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps);
-    else if (D <= 512) layernorm_kernel<16><<<grid, 256, 0, as_stream(stream)>>>(X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps);
-    else layernorm_kernel<32><<<grid, 256, 0, as_stream(stream)>>>(X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps);
+    if (D <= 256) layernorm_kernel<8><<<grid, 256, 0, as_stream(stream)>>>(X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2);
+    else if (D <= 512) layernorm_kernel<16><<<grid, 256, 0, as_stream(stream)>>>(X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2);
+    else layernorm_kernel<32><<<grid, 256, 0, as_stream(stream)>>>(X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2);
     AM_LAUNCH_CHECK("layernorm");
     return AM_OK;
 }

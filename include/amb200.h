@@ -98,18 +98,21 @@ int am_linear_f32(const float* X, int ldx, const float* W, int ldw, float* Y, in
 
 /* Y = LayerNorm(X (+ R)) * gamma + beta, eps inside sqrt (torch.nn.LayerNorm); rows of length D <= 1024 */
 int am_layernorm(const float* X, int ldx, const float* R, int ldr, const float* gamma, const float* beta,
-                 float* Y, int ldy, int M, int D, float eps, am_stream_t stream);
+                 float* Y, int ldy, int M, int D, float eps, void* Y2, int Np2, am_stream_t stream);
+/* (Y2 != NULL additionally writes the bf16 (hi|lo) split [M, 2*Np2] that feeds am_linear_tc; Y may then be NULL) */
 
 /* Multi-head self attention core of torch.nn.TransformerEncoderLayer (models/cmdm.py:66-77,167):
  *   qkv [B,S,3*H*hd] packed (q|k|v), out [B,S,H*hd]; key_pad uint8 [B,S] (1 = ignore key) or NULL;
  *   softmax(q k^T * scale + mask) v.   hd == 64, S <= 512. */
 int am_mha_fwd(const float* qkv, float* out, const uint8_t* key_pad, int B, int S, int H, int hd, float scale,
-               am_stream_t stream);
+               void* out2, am_stream_t stream);
+/* (out2 != NULL additionally writes the bf16 (hi|lo) split [B*S, 2*H*hd]; out may then be NULL) */
 
 /* X[b, row, :] = table[t[b*t_stride], :]  (time token of models/cmdm.py:129,161; table already holds
  * TimestepEmbedder(t) + PE[row] for every t). X is [B, S, D]. */
 int am_gather_time_token(float* X, int S, int D, int row, const float* table, const int32_t* t, int t_stride,
-                         int B, am_stream_t stream);
+                         int B, void* X2, am_stream_t stream);
+/* (X2 != NULL: also writes the row into the bf16 (hi|lo) token buffer [B*S, 2*D]) */
 
 /* dst[i,:] = src[idx[i],:]  (n_p = p[idx.long(), :], pointtransformer.py:62) */
 int am_gather_rows(const float* src, const int32_t* idx, float* dst, int m, int c, am_stream_t stream);
@@ -166,6 +169,20 @@ int am_cdm_decoder_point(const float* x_t, const float* xyz, const float* wd, co
  * linear folded in: contact_layer(h1 + W2 g + b2) = [Wc | Wc W2] [h1 ; g] + (Wc b2 + bc)  (cdm.py:472,511). */
 int am_linear_skinny(const float* X1, int ldx1, int K1, const float* X2, int ldx2, int K2, const float* W,
                      const float* bias, float* Y, int ldy, int M, int N, am_stream_t stream);
+
+/* ------------------------------------------------------------------ tcgen05 tensor-core GEMM
+ * Same contract as am_linear_f32 for the large layers, computed on the 5th-gen tensor cores with
+ * fp32-equivalent accuracy by a 3-term bf16 split (A_lo W_hi + A_hi W_lo + A_hi W_hi), fp32 TMEM
+ * accumulation, TMA-staged SWIZZLE_64B tiles.  A2 [M, 2*Kp] bf16 = (hi | lo) row-major, W2 [N, 2*Kp] bf16 =
+ * (hi | lo); Kp % 32 == 0, zero padded.  Writes fp32 Y (may be NULL) and/or the bf16 (hi|lo) split of Y
+ * (Y2 [rows, 2*Np2], Np2 % 32 == 0, padding columns zeroed) for the next GEMM.  Row map as in am_linear_f32,
+ * plus: a mapped row outside [0, yout_g) is skipped (lets a GEMM over all [B,S] tokens emit only motion rows).
+ * Replaces the cuBLAS GEMMs behind nn.Linear / in_proj / out_proj / linear1 / linear2 (models/cmdm.py:66-77,195)
+ * and the decoder MLP of the Perceiver (models/cdm.py:186, modules.py:651-661). */
+int am_split_bf16(const float* X, int ldx, void* X2, int Kp, int M, int K, am_stream_t stream);
+int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp, const float* bias, int act,
+                 const float* residual, int ldr, int res_mod, float* Y, int ldy, int yin_g, int yout_g, int y_off,
+                 void* Y2, int Np2, am_stream_t stream);
 
 #ifdef __cplusplus
 }
