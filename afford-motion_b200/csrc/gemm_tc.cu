@@ -20,17 +20,16 @@
 // Operand layout in HBM: A2 [M, 2*Kp] bf16 = (hi | lo), W2 [N, 2*Kp] bf16 = (hi | lo), Kp % 32 == 0, zero padded.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 32;
-constexpr int STAGES = 3;
-constexpr int SUB_BYTES = BM * BK * 2;         // 8 KB : one 128x32 bf16 sub-tile
-constexpr int STAGE_BYTES = 4 * SUB_BYTES;     // A_hi, A_lo, W_hi, W_lo
+constexpr int BM = 128, BN = 128;
 constexpr int TMEM_COLS = 128;
 constexpr int TC_THREADS = 256;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int smem_bytes(int BK, int STAGES) { return STAGES * 4 * BM * BK * 2 + 1024 /*align slack*/ + 256 /*barriers*/; }
 
 struct TcParams {
     int M, N, Kp;
@@ -39,6 +38,7 @@ struct TcParams {
     float* Y; int ldy; int yin_g, yout_g, y_off;
     __nv_bfloat16* Y2; int Np2;
     int vecY;
+    long long* dbg;  // optional timeline buffer (tools/tc_timeline.py): CTA (0,0) records clock64() per role
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -91,28 +91,35 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t r[32]) {
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t r[16]) {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr) : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// K-major operand tile in shared memory, SWIZZLE_64B: rows of 32 bf16 (64 B), 8-row groups 512 B apart.
+template <int ACT>
+__device__ __forceinline__ float act_ct(float x) {
+    if (ACT == AM_ACT_GELU) return gelu_erf(x);
+    if (ACT == AM_ACT_SILU) return silu_f(x);
+    if (ACT == AM_ACT_RELU) return fmaxf(x, 0.0f);
+    return x;
+}
+
+// K-major operand tile in shared memory, rows of BK bf16 = one swizzle span (BK=32: SWIZZLE_64B, BK=64: SWIZZLE_128B),
+// 8-row groups 8*row_bytes apart.
 // (cute::UMMA::SmemDescriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout [61,64))
-__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
+template <int BK>
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)1 << 16;                 // LBO (ignored for swizzled K-major; CUTLASS writes 1)
-    d |= (uint64_t)(512 >> 4) << 32;        // SBO = 8 rows * 64 B
-    d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
-    d |= (uint64_t)4 << 61;                 // LayoutType::SWIZZLE_64B
+    d |= (uint64_t)1 << 16;                          // LBO (ignored for swizzled K-major; CUTLASS writes 1)
+    d |= (uint64_t)((8 * BK * 2) >> 4) << 32;        // SBO = 8 rows * row bytes
+    d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+    d |= (uint64_t)(BK == 64 ? 2 : 4) << 61;         // LayoutType::SWIZZLE_128B : SWIZZLE_64B
     return d;
 }
 // cute::UMMA::InstrDescriptor: c_format F32 [4,6)=1 | a_format BF16 [7,10)=1 | b_format BF16 [10,13)=1 | K-major A/B
@@ -127,8 +134,11 @@ __device__ __forceinline__ int64_t map_row_tc(int m, int gin, int gout, int off,
     return (int64_t)(m / gin) * gout + r;
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 2)
+template <int BK, int STAGES, int MINB, int ACT>
+__global__ void __launch_bounds__(TC_THREADS, MINB)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
+    constexpr int SUB_BYTES = BM * BK * 2;      // one 128 x BK bf16 sub-tile
+    constexpr int STAGE_BYTES = 4 * SUB_BYTES;  // A_hi, A_lo, W_hi, W_lo
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -151,10 +161,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 2) tmem_alloc(tmem_holder, TMEM_COLS);
+    if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.dbg[0] = clock64();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.dbg[1] = clock64();
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -163,6 +175,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 int s = kb % STAGES;
                 uint32_t ph = (kb / STAGES) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
+                if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && kb < 64) p.dbg[8 + kb] = clock64();
                 uint8_t* st = smem + s * STAGE_BYTES;
                 mbar_expect_tx(&full[s], STAGE_BYTES);
                 tma_load_2d(st + 0 * SUB_BYTES, &tmA, &full[s], kb * BK, m0);          // A_hi
@@ -178,10 +191,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 int s = kb % STAGES;
                 uint32_t ph = (kb / STAGES) & 1;
                 mbar_wait(&full[s], ph);
+                if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && kb < 64) p.dbg[72 + kb] = clock64();
                 tc_fence_after();
                 uint32_t base = smem_u32(smem + s * STAGE_BYTES);
-                uint64_t a_hi = make_desc_sw64(base), a_lo = make_desc_sw64(base + SUB_BYTES);
-                uint64_t w_hi = make_desc_sw64(base + 2 * SUB_BYTES), w_lo = make_desc_sw64(base + 3 * SUB_BYTES);
+                uint64_t a_hi = make_desc<BK>(base), a_lo = make_desc<BK>(base + SUB_BYTES);
+                uint64_t w_hi = make_desc<BK>(base + 2 * SUB_BYTES), w_lo = make_desc<BK>(base + 3 * SUB_BYTES);
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k) {  // K=16 per MMA -> +32 B inside the 64 B swizzle row (encoded +2)
                     uint64_t ko = (uint64_t)(k * 2);
@@ -191,6 +205,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 umma_commit(&empty[s]);               // stage free once these MMAs retire
                 if (kb == nkb - 1) umma_commit(tmem_full);
+                if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && kb < 64) p.dbg[136 + kb] = clock64();
             }
         }
     } else if (warp >= 4) {
@@ -200,63 +215,93 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int m = m0 + r;
         mbar_wait(tmem_full, 0);
         tc_fence_after();
+        if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 128) p.dbg[2] = clock64();
         bool row_ok = m < p.M, map_ok = true;
         int64_t yrow = row_ok ? map_row_tc(m, p.yin_g, p.yout_g, p.y_off, map_ok) : 0;
         row_ok = row_ok && map_ok;
         const float* rrow = nullptr;
         if (p.residual && row_ok) rrow = p.residual + (p.res_mod > 0 ? (int64_t)(m % p.res_mod) : yrow) * p.ldr;
-        const int act = p.act & 15;
         const bool after = (p.act & AM_ACT_AFTER_RES) != 0;
+        const bool rvec = rrow && ((reinterpret_cast<uintptr_t>(rrow) & 15u) == 0);
+        const bool bvec = p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15u) == 0);
+        // compact epilogue: rolled loop over 16-column groups (keeps the instruction footprint small — a fully unrolled
+        // 128-column epilogue with a runtime activation switch thrashed the instruction cache, see profiles/)
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-            if (!row_ok) continue;
-            const int nb = n0 + c * 32;
-            float f[32];
+        for (int c = 0; c < BN / 16; ++c) {
+            uint32_t v[16];
+            __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent tail of the previous group
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 16), v);
+            const int nb = n0 + c * 16;
+            if (!row_ok || (nb >= p.N && (!p.Y2 || nb >= p.Np2))) continue;
+            float f[16];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                int n = nb + j;
-                float x = __uint_as_float(v[j]);
-                if (n < p.N) {
-                    if (p.bias) x += p.bias[n];
-                    if (after) { if (rrow) x += rrow[n]; x = apply_act(x, act); }
-                    else { x = apply_act(x, act); if (rrow) x += rrow[n]; }
-                } else x = 0.f;
-                f[j] = x;
-            }
-            if (p.Y) {
-                float* dst = p.Y + yrow * p.ldy + nb;
-                if (p.vecY && nb + 31 < p.N) {
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+            const bool full = nb + 15 < p.N;
+            if (p.bias) {
+                if (full && bvec) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                    for (int j = 0; j < 16; j += 4) {
+                        float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
+                        f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                    }
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) if (nb + j < p.N) dst[j] = f[j];
+                    for (int j = 0; j < 16; ++j) if (nb + j < p.N) f[j] += __ldg(p.bias + nb + j);
                 }
             }
-            if (p.Y2 && nb < p.Np2) {  // Np2 % 32 == 0: a chunk is either fully inside the padded width or skipped
+            float rr[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) rr[j] = 0.f;
+            if (rrow) {
+                if (full && rvec && ((nb & 3) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        float4 r4 = *reinterpret_cast<const float4*>(rrow + nb + j);
+                        rr[j] = r4.x; rr[j + 1] = r4.y; rr[j + 2] = r4.z; rr[j + 3] = r4.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) if (nb + j < p.N) rr[j] = rrow[nb + j];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float x = after ? act_ct<ACT>(f[j] + rr[j]) : act_ct<ACT>(f[j]) + rr[j];
+                f[j] = (nb + j < p.N) ? x : 0.f;
+            }
+            if (p.Y && nb < p.N) {
+                float* dst = p.Y + yrow * p.ldy + nb;
+                if (p.vecY && full) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) if (nb + j < p.N) dst[j] = f[j];
+                }
+            }
+            if (p.Y2 && nb < p.Np2) {  // Np2 % 32 == 0: a 16-column group is either inside the padded width or skipped
                 __nv_bfloat16* hi = p.Y2 + yrow * (2 * (int64_t)p.Np2) + nb;
                 __nv_bfloat16* lo = hi + p.Np2;
-                uint32_t ph[16], pl[16];
+                uint32_t ph[8], pl[8];
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
+                for (int j = 0; j < 16; j += 2) {
                     __nv_bfloat16 h0 = __float2bfloat16_rn(f[j]), h1 = __float2bfloat16_rn(f[j + 1]);
                     __nv_bfloat16 l0 = __float2bfloat16_rn(f[j] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(f[j + 1] - __bfloat162float(h1));
                     ph[j / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
                     pl[j / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
                 }
-#pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                    *reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(hi) + j) = make_uint4(ph[j], ph[j + 1], ph[j + 2], ph[j + 3]);
-                    *reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(lo) + j) = make_uint4(pl[j], pl[j + 1], pl[j + 2], pl[j + 3]);
-                }
+                *reinterpret_cast<uint4*>(hi) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                *reinterpret_cast<uint4*>(hi + 8) = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+                *reinterpret_cast<uint4*>(lo) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                *reinterpret_cast<uint4*>(lo + 8) = make_uint4(pl[4], pl[5], pl[6], pl[7]);
             }
         }
     }
+    if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 128) p.dbg[3] = clock64();
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+    if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.dbg[4] = clock64();
 }
 
 // fp32 [M,K] -> bf16 (hi | lo) [M, 2*Kp], zero padded to Kp
@@ -287,8 +332,8 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-// 2-D bf16 tensor [rows, cols] row-major, box = 32 cols x 128 rows, SWIZZLE_64B, OOB -> zeros
-bool make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols) {
+// 2-D bf16 tensor [rows, cols] row-major, box = BK cols x 128 rows, swizzle span = BK*2 bytes, OOB -> zeros
+bool make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, int BK) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
     cuuint64_t gdim[2] = {cols, rows};
@@ -296,14 +341,18 @@ bool make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols) {
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
 
 }  // namespace
 
+static long long* g_tc_dbg = nullptr;
+// debug hook (not part of the public header): timeline buffer of >= 200 int64 for the next am_linear_tc launches
+extern "C" void am_tc_set_debug_(void* buf) { g_tc_dbg = reinterpret_cast<long long*>(buf); }
+
 extern "C" int am_split_bf16(const float* X, int ldx, void* X2, int Kp, int M, int K, am_stream_t stream) {
-    AM_REQUIRE(X && X2 && M > 0 && K > 0 && Kp >= K && Kp % BK == 0 && ldx >= K, AM_EINVAL, "am_split_bf16: bad args (Kp % 32 == 0)");
+    AM_REQUIRE(X && X2 && M > 0 && K > 0 && Kp >= K && Kp % 32 == 0 && ldx >= K, AM_EINVAL, "am_split_bf16: bad args (Kp % 32 == 0)");
     int64_t total = (int64_t)M * Kp;
     int64_t blocks = (total + 255) / 256;
     int grid = (int)(blocks < (int64_t)AM_NUM_SMS * 8 ? blocks : (int64_t)AM_NUM_SMS * 8);
@@ -315,28 +364,55 @@ extern "C" int am_split_bf16(const float* X, int ldx, void* X2, int Kp, int M, i
 extern "C" int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp, const float* bias, int act, const float* residual, int ldr,
                             int res_mod, float* Y, int ldy, int yin_g, int yout_g, int y_off, void* Y2, int Np2, am_stream_t stream) {
     AM_REQUIRE(A2 && W2 && (Y || Y2), AM_EINVAL, "am_linear_tc: null pointer");
-    AM_REQUIRE(M > 0 && N > 0 && Kp > 0 && Kp % BK == 0, AM_EINVAL, "am_linear_tc: Kp must be a positive multiple of 32");
+    AM_REQUIRE(M > 0 && N > 0 && Kp > 0 && Kp % 32 == 0, AM_EINVAL, "am_linear_tc: Kp must be a positive multiple of 32");
     AM_REQUIRE((act & 15) <= 3 && (act & ~31) == 0, AM_EINVAL, "am_linear_tc: bad activation");
     AM_REQUIRE(!Y || ldy >= N, AM_EINVAL, "am_linear_tc: bad ldy");
     AM_REQUIRE(!Y2 || (Np2 >= N && Np2 % 32 == 0), AM_EINVAL, "am_linear_tc: Np2 must be a multiple of 32 and >= N");
     AM_REQUIRE(!residual || ldr >= N, AM_EINVAL, "am_linear_tc: bad residual stride");
     AM_REQUIRE((reinterpret_cast<uintptr_t>(A2) & 15u) == 0 && (reinterpret_cast<uintptr_t>(W2) & 15u) == 0 &&
                (!Y2 || (reinterpret_cast<uintptr_t>(Y2) & 15u) == 0), AM_EALIGN, "am_linear_tc: operands must be 16-byte aligned");
-    CUtensorMap tmA, tmB;
-    AM_REQUIRE(make_map(&tmA, A2, (uint64_t)M, (uint64_t)2 * Kp), AM_ELAUNCH, "am_linear_tc: cuTensorMapEncodeTiled(A) failed");
-    AM_REQUIRE(make_map(&tmB, W2, (uint64_t)N, (uint64_t)2 * Kp), AM_ELAUNCH, "am_linear_tc: cuTensorMapEncodeTiled(W) failed");
-    static bool attr = false;
-    if (!attr) {
-        if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
-            am_set_error_("am_linear_tc: shared memory opt-in failed");
-            return AM_ELAUNCH;
-        }
-        attr = true;
+    // kernel variant (tuning knob, read once): "32x3" (default: BK=32, 3 stages, 2 CTAs/SM), "32x6", "64x3" (1 CTA/SM)
+    static int variant = -1;
+    if (variant < 0) {
+        const char* e = getenv("AMB200_TC_VARIANT");
+        variant = 0;
+        if (e && !strcmp(e, "32x6")) variant = 1;
+        if (e && !strcmp(e, "64x3")) variant = 2;
     }
-    TcParams p{M, N, Kp, bias, act, residual, ldr, res_mod, Y, ldy, yin_g, yout_g, y_off, reinterpret_cast<__nv_bfloat16*>(Y2), Np2, 0};
+    const int BKsel = variant == 2 ? 64 : 32;
+    AM_REQUIRE(Kp % BKsel == 0, AM_EINVAL, "am_linear_tc: Kp must be a multiple of the K block");
+    CUtensorMap tmA, tmB;
+    AM_REQUIRE(make_map(&tmA, A2, (uint64_t)M, (uint64_t)2 * Kp, BKsel), AM_ELAUNCH, "am_linear_tc: cuTensorMapEncodeTiled(A) failed");
+    AM_REQUIRE(make_map(&tmB, W2, (uint64_t)N, (uint64_t)2 * Kp, BKsel), AM_ELAUNCH, "am_linear_tc: cuTensorMapEncodeTiled(W) failed");
+    TcParams p{M, N, Kp, bias, act, residual, ldr, res_mod, Y, ldy, yin_g, yout_g, y_off, reinterpret_cast<__nv_bfloat16*>(Y2), Np2, 0, g_tc_dbg};
     p.vecY = Y && (reinterpret_cast<uintptr_t>(Y) & 15u) == 0 && (ldy % 4 == 0);
     dim3 grid(cdiv(N, BN), cdiv(M, BM));
-    gemm_tc_kernel<<<grid, TC_THREADS, SMEM_BYTES, as_stream(stream)>>>(tmA, tmB, p);
+    cudaStream_t st = as_stream(stream);
+#define AM_TC_LAUNCH(BK_, ST_, MB_, ACT_)                                                                                     \
+    do {                                                                                                                      \
+        static bool attr_ = false;                                                                                            \
+        if (!attr_) {                                                                                                         \
+            if (cudaFuncSetAttribute(gemm_tc_kernel<BK_, ST_, MB_, ACT_>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                     smem_bytes(BK_, ST_)) != cudaSuccess) {                                                  \
+                am_set_error_("am_linear_tc: shared memory opt-in failed");                                                   \
+                return AM_ELAUNCH;                                                                                            \
+            }                                                                                                                 \
+            attr_ = true;                                                                                                     \
+        }                                                                                                                     \
+        gemm_tc_kernel<BK_, ST_, MB_, ACT_><<<grid, TC_THREADS, smem_bytes(BK_, ST_), st>>>(tmA, tmB, p);                      \
+    } while (0)
+#define AM_TC_BY_ACT(BK_, ST_, MB_)                                   \
+    switch (act & 15) {                                               \
+        case AM_ACT_GELU: AM_TC_LAUNCH(BK_, ST_, MB_, AM_ACT_GELU); break; \
+        case AM_ACT_SILU: AM_TC_LAUNCH(BK_, ST_, MB_, AM_ACT_SILU); break; \
+        case AM_ACT_RELU: AM_TC_LAUNCH(BK_, ST_, MB_, AM_ACT_RELU); break; \
+        default: AM_TC_LAUNCH(BK_, ST_, MB_, AM_ACT_NONE); break;      \
+    }
+    if (variant == 0) { AM_TC_BY_ACT(32, 3, 2) }
+    else if (variant == 1) { AM_TC_BY_ACT(32, 6, 1) }
+    else { AM_TC_BY_ACT(64, 3, 1) }
+#undef AM_TC_BY_ACT
+#undef AM_TC_LAUNCH
     AM_LAUNCH_CHECK("linear_tc");
     return AM_OK;
 }

@@ -212,14 +212,14 @@ def test_linear_tc_row_maps():
     ops.linear_tc(a2, w2, B * T, N, 64, y=y, residual=_cuda(pe), ldr=N, res_mod=T, ymap=(T, S, off))
     ref = torch.zeros(B, S, N)
     ref[:, off:] = (x.double() @ w.double().T).float().view(B, T, N) + pe
-    assert (y.cpu() - ref).abs().max() < 1e-4
+    assert (y.cpu() - ref).abs().max() < 2e-5 * ref.abs().max()  # |y| ~ 10 here (unnormalised weights)
     # inverse (skip) map: GEMM over all [B,S] rows, only rows s >= off are written to a [B,T] output
     xs = torch.randn(B * S, K, generator=g)
     a3 = ops.split_bf16(_cuda(xs), B * S, K)
     out = torch.full((B, T, N), 7.0, device=DEV)
     ops.linear_tc(a3, w2, B * S, N, 64, y=out, ymap=(S, T, -off))
     ref2 = (xs.double() @ w.double().T).float().view(B, S, N)[:, off:]
-    assert (out.cpu() - ref2).abs().max() < 1e-4
+    assert (out.cpu() - ref2).abs().max() < 2e-5 * ref2.abs().max()
 
 
 def test_linear_row_maps():

@@ -1,0 +1,28 @@
+"""Per-role clock64 timeline of CTA (0,0) of the tcgen05 GEMM (debug hook am_tc_set_debug_)."""
+import os, sys, ctypes
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "afford-motion_b200"))
+import torch
+from amb200 import ops, lib
+dev = "cuda:0"
+M, N, K = 32 * 326, 1536, 512
+g = torch.Generator(device=dev).manual_seed(0)
+x, w = torch.randn(M, K, device=dev, generator=g), torch.randn(N, K, device=dev, generator=g) / 22
+xs, wsp = ops.split_bf16(x, M, K), ops.split_bf16(w, N, K)
+y = torch.empty(M, N, device=dev)
+L = lib.load()
+L.am_tc_set_debug_.argtypes = [ctypes.c_void_p]
+for _ in range(3):
+    ops.linear_tc(xs, wsp, M, N, K, y=y)
+dbg = torch.zeros(256, dtype=torch.int64, device=dev)
+L.am_tc_set_debug_(dbg.data_ptr())
+ops.linear_tc(xs, wsp, M, N, K, y=y)
+torch.cuda.synchronize()
+L.am_tc_set_debug_(None)
+d = dbg.cpu().tolist()
+t0 = d[0]
+nkb = K // (64 if os.environ.get("AMB200_TC_VARIANT") == "64x3" else 32)
+print("prologue sync done +", d[1] - t0, " tmem_full seen +", d[2] - t0, " epilogue done +", d[3] - t0, " teardown +", d[4] - t0)
+print("kb  tma_issue  full_seen  mma_issued(commit)")
+for kb in range(nkb):
+    print(kb, d[8 + kb] - t0, d[72 + kb] - t0, d[136 + kb] - t0)
