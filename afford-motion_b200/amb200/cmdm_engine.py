@@ -40,6 +40,9 @@ class CMDMEngine:
         # "tc": tcgen05 3-term bf16-split GEMMs (default); "simt": fp32 SIMT GEMMs (cross-check path)
         self.gemm = os.environ.get("AMB200_GEMM", "tc")
         assert self.gemm in ("tc", "simt")
+        # "tc": tcgen05 attention (default with the tc GEMM path, S <= 384); "simt": fp32 SIMT attention kernel
+        self.attn = os.environ.get("AMB200_ATTN", "tc")
+        assert self.attn in ("tc", "simt")
 
     # ------------------------------------------------------------------ weights
     def refresh(self):
@@ -137,7 +140,7 @@ class CMDMEngine:
             if self.gemm == "tc":
                 bf = lambda r, c: torch.zeros(r, c, dtype=torch.bfloat16, device=dev)
                 ws.update({"X0S": bf(M, 2 * D), "XSa": bf(M, 2 * D), "XSb": bf(M, 2 * D), "ATTS": bf(M, 2 * D), "Y1S": bf(M, 2 * D),
-                           "FFS": bf(M, 2 * ops.pad32(ff)), "xS": None})
+                           "FFS": bf(M, 2 * ops.pad32(ff)), "xS": None, "QKVS": bf(M, 6 * D)})
             self._ws[key] = ws
         return ws
 
@@ -216,8 +219,12 @@ class CMDMEngine:
             p = f"l{i}."
             last = i == self.nlayers - 1
             nxt, nxtS = (ws["Xa"], ws["XSa"]) if i % 2 == 0 else (ws["Xb"], ws["XSb"])
-            ops.linear_tc(curS, w[p + "in_w2"], M, 3 * D, D, y=ws["QKV"], bias=w[p + "in_b"])
-            ops.mha_fwd(ws["QKV"], None, cond.key_pad, B, S, H, hd, 1.0 / math.sqrt(hd), out2=ws["ATTS"])
+            if self.attn == "tc" and S <= 384 and hd == 64:
+                ops.linear_tc(curS, w[p + "in_w2"], M, 3 * D, D, y2=ws["QKVS"], bias=w[p + "in_b"], Np2=3 * D)
+                ops.mha_tc_fwd(ws["QKVS"], None, ws["ATTS"], cond.key_pad, B, S, H, hd, 1.0 / math.sqrt(hd))
+            else:
+                ops.linear_tc(curS, w[p + "in_w2"], M, 3 * D, D, y=ws["QKV"], bias=w[p + "in_b"])
+                ops.mha_fwd(ws["QKV"], None, cond.key_pad, B, S, H, hd, 1.0 / math.sqrt(hd), out2=ws["ATTS"])
             ops.linear_tc(ws["ATTS"], w[p + "out_w2"], M, D, D, y=ws["TMP"], bias=w[p + "out_b"], residual=cur)
             ops.layernorm(ws["TMP"], w[p + "n1g"], w[p + "n1b"], ws["Y1"], M, D, eps=w[p + "eps1"], y2=ws["Y1S"])
             ops.linear_tc(ws["Y1S"], w[p + "w12"], M, self.ff, D, y2=ws["FFS"], bias=w[p + "b1"], act="gelu", Np2=ffp)

@@ -100,6 +100,14 @@ def mha_fwd(qkv, out, key_pad_u8, B, S, H, hd, scale, out2=None):
     return out
 
 
+def mha_tc_fwd(qkv2, out, out2, key_pad_u8, B, S, H, hd, scale):
+    """tcgen05 attention on the bf16 (hi|lo) QKV written by the in_proj GEMM (see am_mha_tc_fwd)."""
+    _chk_cuda(qkv2)
+    _l.check(_l.load().am_mha_tc_fwd(_ptr(qkv2), _ptr(out), _ptr(out2), _ptr(key_pad_u8), B, S, H, hd, float(scale), _stream()),
+             "am_mha_tc_fwd")
+    return out if out is not None else out2
+
+
 def gather_time_token(X, S, D, row, table, t, t_stride, B, x2=None):
     _l.check(_l.load().am_gather_time_token(_ptr(X), S, D, row, _ptr(table), _ptr(t), t_stride, B, _ptr(x2), _stream()),
              "am_gather_time_token")
@@ -220,6 +228,9 @@ def _flops_of(name, args, kwargs):
         return 2.0 * M * N * K
     if name == "linear_tc":
         return 2.0 * args[2] * args[3] * args[4]
+    if name == "mha_tc_fwd":
+        B, S, H, hd = args[4], args[5], args[6], args[7]
+        return 4.0 * B * H * S * S * hd
     if name == "mha_fwd":
         B, S, H, hd = args[3], args[4], args[5], args[6]
         return 4.0 * B * H * S * S * hd
@@ -244,5 +255,5 @@ def _wrap(name, fn):
 
 for _n in ("randn_", "p_sample_update", "ddim_update", "q_sample", "masked_mse", "add_i32", "linear", "layernorm", "mha_fwd",
            "gather_time_token", "gather_rows", "furthestsampling", "knnquery", "pt_layer_fwd", "transition_down_fwd",
-           "cdm_encoder_partial", "cdm_encoder_combine", "cdm_decoder_point", "linear_skinny", "split_bf16", "linear_tc"):
+           "cdm_encoder_partial", "cdm_encoder_combine", "cdm_decoder_point", "linear_skinny", "split_bf16", "linear_tc", "mha_tc_fwd"):
     globals()[_n] = _wrap(_n, globals()[_n])

@@ -184,6 +184,14 @@ int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp, const flo
                  const float* residual, int ldr, int res_mod, float* Y, int ldy, int yin_g, int yout_g, int y_off,
                  void* Y2, int Np2, am_stream_t stream);
 
+/* tcgen05 multi-head self-attention (S <= 384, head dim 64): softmax(q k^T * scale + key mask) v per (batch, head),
+ * fp32-equivalent accuracy (3-term bf16 split, fp32 TMEM accumulation, exact softmax — the whole key row lives in TMEM,
+ * P is fed to the PV MMA straight from TMEM).  qkv2 [B*S, 2*3*H*64] bf16 = (hi | lo) x (q|k|v) as written by the in_proj
+ * am_linear_tc epilogue; out fp32 [B*S, H*64] and/or out2 bf16 (hi|lo) [B*S, 2*H*64]; key_pad uint8 [B,S] or NULL.
+ * Replaces the SDPA / native-MHA library call inside torch.nn.TransformerEncoderLayer (models/cmdm.py:66-77,167). */
+int am_mha_tc_fwd(const void* qkv2, float* out, void* out2, const uint8_t* key_pad, int B, int S, int H, int hd,
+                  float scale, am_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

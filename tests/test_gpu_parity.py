@@ -259,6 +259,36 @@ def test_layernorm_and_attention_vs_torch():
         assert (out.cpu().double() - ref).abs().max() < 2e-5
 
 
+@pytest.mark.parametrize("B,S", [(3, 326), (2, 212), (1, 130), (2, 384), (1, 40)])
+def test_mha_tc_vs_fp64(B, S):
+    """tcgen05 attention (P in TMEM, 3-term bf16 split) vs an fp64 softmax(QK^T/8 + mask)V reference."""
+    g = torch.Generator().manual_seed(S)
+    H, hd = 8, 64
+    qkv = torch.randn(B * S, 3 * H * hd, generator=g)
+    pad = torch.zeros(B, S, dtype=torch.bool)
+    if S > 50:
+        pad[0, S - 37:] = True
+        pad[-1, 1] = True
+        pad[-1, 5:9] = True
+    qkv2 = ops.split_bf16(_cuda(qkv), B * S, 3 * H * hd)
+    out = torch.full((B * S, H * hd), float("nan"), device=DEV)
+    out2 = torch.zeros(B * S, 2 * H * hd, dtype=torch.bfloat16, device=DEV)
+    ops.mha_tc_fwd(qkv2, out, out2, _cuda(pad.to(torch.uint8)), B, S, H, hd, hd ** -0.5)
+    q, k, v = (t.view(B, S, H, hd).transpose(1, 2).double() for t in qkv.view(B, S, -1).split(H * hd, -1))
+    sc = (q @ k.transpose(-1, -2)) * hd ** -0.5
+    sc = sc.masked_fill(pad[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(sc, -1) @ v).transpose(1, 2).reshape(B * S, H * hd)
+    err = (out.cpu().double() - ref).abs().max().item()
+    assert err < 5e-5, err
+    o2 = out2.float().cpu()
+    assert (o2[:, :H * hd] + o2[:, H * hd:] - out.cpu()).abs().max() < 1e-4
+    # agreement with the fp32 SIMT attention kernel (S <= 352 there)
+    if S <= 352:
+        o1 = torch.empty(B, S, H * hd, device=DEV)
+        ops.mha_fwd(_cuda(qkv.view(B, S, -1)), o1, _cuda(pad.to(torch.uint8)), B, S, H, hd, hd ** -0.5)
+        assert (o1.view(B * S, -1) - out).abs().max() < 5e-5
+
+
 # ------------------------------------------------------------------ network parity vs reference-generated goldens
 @pytest.mark.parametrize("N", [1024, 8192])
 def test_cmdm_forward_matches_reference(golden_dir, cmdm_models, N):
