@@ -29,6 +29,7 @@ namespace {
 constexpr int BM = 128, BN = 128;
 constexpr int TMEM_COLS = 128;
 constexpr int TC_THREADS = 256;
+constexpr int TCP_THREADS = 384;  // persistent kernel: 4 control warps + 8 epilogue warps
 constexpr int smem_bytes(int BK, int STAGES) { return STAGES * 4 * BM * BK * 2 + 1024 /*align slack*/ + 256 /*barriers*/; }
 
 struct TcParams {
@@ -49,6 +50,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
@@ -134,88 +138,14 @@ __device__ __forceinline__ int64_t map_row_tc(int m, int gin, int gout, int off,
     return (int64_t)(m / gin) * gout + r;
 }
 
-template <int BK, int STAGES, int MINB, int ACT>
-__global__ void __launch_bounds__(TC_THREADS, MINB)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
-    constexpr int SUB_BYTES = BM * BK * 2;      // one 128 x BK bf16 sub-tile
-    constexpr int STAGE_BYTES = 4 * SUB_BYTES;  // A_hi, A_lo, W_hi, W_lo
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-    uint64_t* empty = full + STAGES;
-    uint64_t* tmem_full = empty + STAGES;
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_full + 1);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int nkb = p.Kp / BK;
-
-    if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
-    }
-    if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(tmem_full, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    if (warp == 2) tmem_alloc(tmem_holder, TMEM_COLS);
-    if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.dbg[0] = clock64();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_holder;
-    if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.dbg[1] = clock64();
-
-    if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            for (int kb = 0; kb < nkb; ++kb) {
-                int s = kb % STAGES;
-                uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && kb < 64) p.dbg[8 + kb] = clock64();
-                uint8_t* st = smem + s * STAGE_BYTES;
-                mbar_expect_tx(&full[s], STAGE_BYTES);
-                tma_load_2d(st + 0 * SUB_BYTES, &tmA, &full[s], kb * BK, m0);          // A_hi
-                tma_load_2d(st + 1 * SUB_BYTES, &tmA, &full[s], p.Kp + kb * BK, m0);   // A_lo
-                tma_load_2d(st + 2 * SUB_BYTES, &tmB, &full[s], kb * BK, n0);          // W_hi
-                tma_load_2d(st + 3 * SUB_BYTES, &tmB, &full[s], p.Kp + kb * BK, n0);   // W_lo
-            }
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer (single thread) =====================
-        if (lane == 0) {
-            for (int kb = 0; kb < nkb; ++kb) {
-                int s = kb % STAGES;
-                uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&full[s], ph);
-                if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && kb < 64) p.dbg[72 + kb] = clock64();
-                tc_fence_after();
-                uint32_t base = smem_u32(smem + s * STAGE_BYTES);
-                uint64_t a_hi = make_desc<BK>(base), a_lo = make_desc<BK>(base + SUB_BYTES);
-                uint64_t w_hi = make_desc<BK>(base + 2 * SUB_BYTES), w_lo = make_desc<BK>(base + 3 * SUB_BYTES);
-#pragma unroll
-                for (int k = 0; k < BK / 16; ++k) {  // K=16 per MMA -> +32 B inside the 64 B swizzle row (encoded +2)
-                    uint64_t ko = (uint64_t)(k * 2);
-                    umma_bf16(tmem_base, a_lo + ko, w_hi + ko, IDESC, (kb | k) ? 1u : 0u);
-                    umma_bf16(tmem_base, a_hi + ko, w_lo + ko, IDESC, 1u);
-                    umma_bf16(tmem_base, a_hi + ko, w_hi + ko, IDESC, 1u);
-                }
-                umma_commit(&empty[s]);               // stage free once these MMAs retire
-                if (kb == nkb - 1) umma_commit(tmem_full);
-                if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && kb < 64) p.dbg[136 + kb] = clock64();
-            }
-        }
-    } else if (warp >= 4) {
-        // ===================== epilogue: one accumulator row per thread =====================
-        const int q = warp & 3;
-        const int r = q * 32 + lane;
-        const int m = m0 + r;
-        mbar_wait(tmem_full, 0);
-        tc_fence_after();
-        if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 128) p.dbg[2] = clock64();
+// Epilogue of one accumulator tile: thread (q, lane) owns accumulator row r = 32q + lane of the 128-row tile whose first
+// TMEM column is `tmem_tile`; NCOLS output columns starting at global column n0.  bias / activation / residual / token
+// row map, fp32 store and/or bf16 (hi|lo) split store.
+template <int ACT, int NCOLS>
+__device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_tile, int m0, int n0, int q, int lane) {
+    const int m = m0 + q * 32 + lane;
+    const uint32_t tmem_base = tmem_tile;
+    constexpr int BN = NCOLS;
         bool row_ok = m < p.M, map_ok = true;
         int64_t yrow = row_ok ? map_row_tc(m, p.yin_g, p.yout_g, p.y_off, map_ok) : 0;
         row_ok = row_ok && map_ok;
@@ -296,12 +226,358 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 *reinterpret_cast<uint4*>(lo + 8) = make_uint4(pl[4], pl[5], pl[6], pl[7]);
             }
         }
+    
+}
+
+// Coalesced epilogue (persistent kernel).  8 epilogue warps: warp (q, half) owns accumulator rows [32q, 32q+32) and the
+// column half [half*NCOLS/2, ...).  Each 32x32 sub-block is transposed through a per-warp 4 KB staging buffer (16-byte
+// chunks XOR-swizzled by row, conflict-free both ways) so that one warp instruction covers TWO whole row segments:
+// lanes 0-15 -> row 2i, lanes 16-31 -> row 2i+1, lane & 15 = column pair -> 128 B fp32 / 64 B bf16 contiguous per row.
+// Branch-free row loop (predicated accesses only) so the compiler can software-pipeline the shared/global loads.
+template <int ACT, int NCOLS>
+__device__ __forceinline__ void epilogue_tile_coalesced(const TcParams& p, uint32_t tmem_tile, int m0, int n0, int q, int half, int lane,
+                                                        float* stage /* this warp's 32 x 32 fp32 buffer */) {
+    const unsigned FULL = 0xffffffffu;
+    const int m_own = m0 + q * 32 + lane;
+    bool row_ok = m_own < p.M, map_ok = true;
+    int64_t yrow64 = row_ok ? map_row_tc(m_own, p.yin_g, p.yout_g, p.y_off, map_ok) : 0;
+    row_ok = row_ok && map_ok;
+    const unsigned okmask = __ballot_sync(FULL, row_ok);
+    const int yrow_own = (int)yrow64;
+    const int rres_own = p.res_mod > 0 ? (m_own % p.res_mod) : (int)yrow64;
+    const bool after = (p.act & AM_ACT_AFTER_RES) != 0;
+    const bool y_v2 = p.Y && ((reinterpret_cast<uintptr_t>(p.Y) & 7u) == 0) && (p.ldy % 2 == 0);
+    const bool r_v2 = p.residual && ((reinterpret_cast<uintptr_t>(p.residual) & 7u) == 0) && (p.ldr % 2 == 0);
+    const int rsel = lane >> 4, cp = lane & 15;
+    const long long dflags = p.dbg ? p.dbg[255] : 0;  // timeline experiments only: 1 = no global stores, 2 = no tcgen05.ld, 4 = skip phase 2
+#pragma unroll 1
+    for (int blk = 0; blk < NCOLS / 64; ++blk) {
+        const int col0 = half * (NCOLS / 2) + blk * 32;  // first column of this 32-wide sub-block inside the tile
+        const int nblk0 = n0 + col0;
+        const bool any_col = nblk0 < p.N || (p.Y2 && nblk0 < p.Np2);
+        __syncwarp();
+        // phase 1: TMEM (lane = row) -> staging, 8 chunks of 16 B per row, chunk' = chunk ^ (row & 7)
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            uint32_t v[16];
+            if (!(dflags & 2)) tmem_ld16(tmem_tile + ((uint32_t)(q * 32) << 16) + (uint32_t)(col0 + g * 16), v);
+            else { for (int z = 0; z < 16; ++z) v[z] = 0; }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int c4 = g * 4 + k;
+                *reinterpret_cast<uint4*>(stage + lane * 32 + ((c4 ^ (lane & 7)) << 2)) = make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+            }
+        }
+        __syncwarp();
+        if (!any_col || (dflags & 4)) continue;
+        // phase 2: lane = (row parity, column pair)
+        const int n = nblk0 + 2 * cp;
+        const bool c0ok = n < p.N, c1ok = n + 1 < p.N;
+        float b0 = 0.f, b1 = 0.f;
+        if (p.bias) { if (c0ok) b0 = __ldg(p.bias + n); if (c1ok) b1 = __ldg(p.bias + n + 1); }
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+            const int r = 2 * i + rsel;
+            const int yrow = __shfl_sync(FULL, yrow_own, r);
+            const int rres = __shfl_sync(FULL, rres_own, r);
+            const bool ok = (okmask >> r) & 1u;
+            const float2 xv = *reinterpret_cast<const float2*>(stage + r * 32 + (((cp >> 1) ^ (r & 7)) << 2) + ((cp & 1) << 1));
+            float x0 = xv.x + b0, x1 = xv.y + b1;
+            float r0 = 0.f, r1 = 0.f;
+            if (p.residual && ok) {
+                const float* rp = p.residual + (int64_t)rres * p.ldr + n;
+                if (r_v2 && c1ok) { const float2 t = *reinterpret_cast<const float2*>(rp); r0 = t.x; r1 = t.y; }
+                else { if (c0ok) r0 = rp[0]; if (c1ok) r1 = rp[1]; }
+            }
+            if (after) { x0 = act_ct<ACT>(x0 + r0); x1 = act_ct<ACT>(x1 + r1); }
+            else { x0 = act_ct<ACT>(x0) + r0; x1 = act_ct<ACT>(x1) + r1; }
+            x0 = c0ok ? x0 : 0.f;
+            x1 = c1ok ? x1 : 0.f;
+            if (p.Y && ok && c0ok && !(dflags & 1)) {
+                float* dst = p.Y + (int64_t)yrow * p.ldy + n;
+                if (y_v2 && c1ok) *reinterpret_cast<float2*>(dst) = make_float2(x0, x1);
+                else { dst[0] = x0; if (c1ok) dst[1] = x1; }
+            }
+            if (p.Y2 && ok && n < p.Np2) {
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+                uint32_t* hi = reinterpret_cast<uint32_t*>(p.Y2 + (int64_t)yrow * (2 * (int64_t)p.Np2) + n);
+                hi[0] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                hi[p.Np2 / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            }
+        }
+    }
+}
+
+// Fast-path epilogue (the four big CMDM GEMMs): no row map, no broadcast residual, tile entirely inside N, even strides.
+// MODE 1: bias (+act) -> bf16 (hi|lo) only (in_proj, FFN1);  MODE 2: bias + fp32 residual -> fp32 only (out_proj, FFN2).
+// Everything that is loop-invariant is hoisted and all 16 shared / residual loads of a 32x32 block are issued before the
+// first dependent instruction, so the two epilogue warps of a scheduler keep several memory operations in flight.
+template <int ACT, int NCOLS, int MODE>
+__device__ __forceinline__ void epilogue_tile_fast(const TcParams& p, uint32_t tmem_tile, int m0, int n0, int q, int half, int lane,
+                                                   uint32_t stage_u32) {
+    const int m_base = m0 + q * 32;
+    const int rows_valid = p.M - m_base;  // rows r < rows_valid exist
+    const int rsel = lane >> 4, cp = lane & 15;
+#pragma unroll 1
+    for (int blk = 0; blk < NCOLS / 64; ++blk) {
+        const int col0 = half * (NCOLS / 2) + blk * 32;
+        const int n = n0 + col0 + 2 * cp;
+        __syncwarp();
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            uint32_t v[16];
+            tmem_ld16(tmem_tile + ((uint32_t)(q * 32) << 16) + (uint32_t)(col0 + g * 16), v);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int c4 = g * 4 + k;
+                const uint32_t a = stage_u32 + lane * 128 + ((c4 ^ (lane & 7)) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v[4 * k]), "r"(v[4 * k + 1]), "r"(v[4 * k + 2]), "r"(v[4 * k + 3]) : "memory");
+            }
+        }
+        __syncwarp();
+        float2 bv = make_float2(0.f, 0.f);
+        if (p.bias) bv = __ldg(reinterpret_cast<const float2*>(p.bias + n));
+        float2 xv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int r = 2 * i + rsel;
+            const uint32_t a = stage_u32 + r * 128 + (((cp >> 1) ^ (r & 7)) << 4) + ((cp & 1) << 3);
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(xv[i].x), "=f"(xv[i].y) : "r"(a) : "memory");
+        }
+        if (MODE == 2) {
+            float2 rv[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int r = 2 * i + rsel;
+                rv[i] = make_float2(0.f, 0.f);
+                if (r < rows_valid) rv[i] = *reinterpret_cast<const float2*>(p.residual + (int64_t)(m_base + r) * p.ldr + n);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int r = 2 * i + rsel;
+                const float x0 = act_ct<ACT>(xv[i].x + bv.x) + rv[i].x, x1 = act_ct<ACT>(xv[i].y + bv.y) + rv[i].y;
+                if (r < rows_valid) *reinterpret_cast<float2*>(p.Y + (int64_t)(m_base + r) * p.ldy + n) = make_float2(x0, x1);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int r = 2 * i + rsel;
+                const float x0 = act_ct<ACT>(xv[i].x + bv.x), x1 = act_ct<ACT>(xv[i].y + bv.y);
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+                if (r < rows_valid) {
+                    uint32_t* hi = reinterpret_cast<uint32_t*>(p.Y2 + (int64_t)(m_base + r) * (2 * (int64_t)p.Np2) + n);
+                    hi[0] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                    hi[p.Np2 / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                }
+            }
+        }
+    }
+}
+
+template <int BK, int STAGES, int MINB, int ACT>
+__global__ void __launch_bounds__(TC_THREADS, MINB)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
+    constexpr int SUB_BYTES = BM * BK * 2;      // one 128 x BK bf16 sub-tile
+    constexpr int STAGE_BYTES = 4 * SUB_BYTES;  // A_hi, A_lo, W_hi, W_lo
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int nkb = p.Kp / BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc(tmem_holder, TMEM_COLS);
+    if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.dbg[0] = clock64();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+    if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.dbg[1] = clock64();
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                int s = kb % STAGES;
+                uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && kb < 64) p.dbg[8 + kb] = clock64();
+                uint8_t* st = smem + s * STAGE_BYTES;
+                mbar_expect_tx(&full[s], STAGE_BYTES);
+                tma_load_2d(st + 0 * SUB_BYTES, &tmA, &full[s], kb * BK, m0);          // A_hi
+                tma_load_2d(st + 1 * SUB_BYTES, &tmA, &full[s], p.Kp + kb * BK, m0);   // A_lo
+                tma_load_2d(st + 2 * SUB_BYTES, &tmB, &full[s], kb * BK, n0);          // W_hi
+                tma_load_2d(st + 3 * SUB_BYTES, &tmB, &full[s], p.Kp + kb * BK, n0);   // W_lo
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (single thread) =====================
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                int s = kb % STAGES;
+                uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && kb < 64) p.dbg[72 + kb] = clock64();
+                tc_fence_after();
+                uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+                uint64_t a_hi = make_desc<BK>(base), a_lo = make_desc<BK>(base + SUB_BYTES);
+                uint64_t w_hi = make_desc<BK>(base + 2 * SUB_BYTES), w_lo = make_desc<BK>(base + 3 * SUB_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {  // K=16 per MMA -> +32 B inside the 64 B swizzle row (encoded +2)
+                    uint64_t ko = (uint64_t)(k * 2);
+                    umma_bf16(tmem_base, a_lo + ko, w_hi + ko, IDESC, (kb | k) ? 1u : 0u);
+                    umma_bf16(tmem_base, a_hi + ko, w_lo + ko, IDESC, 1u);
+                    umma_bf16(tmem_base, a_hi + ko, w_hi + ko, IDESC, 1u);
+                }
+                umma_commit(&empty[s]);               // stage free once these MMAs retire
+                if (kb == nkb - 1) umma_commit(tmem_full);
+                if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && kb < 64) p.dbg[136 + kb] = clock64();
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: one accumulator row per thread =====================
+        const int q = warp & 3;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 128) p.dbg[2] = clock64();
+        epilogue_tile<ACT, 128>(p, tmem_base, m0, n0, q, lane);
     }
     if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 128) p.dbg[3] = clock64();
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
     if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.dbg[4] = clock64();
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Persistent variant (default): one CTA per SM loops over output tiles (tile = m_tile * n_tiles + n_tile, static
+// round-robin), BM = 128, BN_ in {128, 256}, K-block 32.  The smem ring runs continuously ACROSS tiles (NST stages of
+// {A_hi, A_lo, W_hi, W_lo}; 192 KB in flight so the ~2000-cycle TMA latency is covered), and the accumulator is
+// double-buffered in TMEM (2 x BN_ columns) so the epilogue of tile i overlaps the main loop of tile i+1.
+template <int BN_, int NST, int ACT, int MODE>
+__global__ void __launch_bounds__(TCP_THREADS, 1)
+gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p, int n_tiles,
+                          int total_tiles) {
+    constexpr int BK = 32;
+    constexpr int A_SUB = BM * BK * 2;          // 8 KB
+    constexpr int B_SUB = BN_ * BK * 2;         // 8 / 16 KB
+    constexpr int STAGE_BYTES = 2 * A_SUB + 2 * B_SUB;
+    constexpr uint32_t IDESC_P = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN_ >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + NST * STAGE_BYTES);
+    uint64_t* empty = full + NST;
+    uint64_t* tmem_full = empty + NST;     // [2]
+    uint64_t* tmem_empty = tmem_full + 2;  // [2]
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* stage_buf = reinterpret_cast<float*>(smem + NST * STAGE_BYTES + 256);  // 8 warps x 32 x 32 fp32 (epilogue transpose)
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkb = p.Kp / BK;
+    const bool dbg = p.dbg && blockIdx.x == 0;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 256); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc(tmem_holder, 2 * BN_);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+    if (dbg && threadIdx.x == 0) p.dbg[0] = clock64();
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t kbc = 0;  // running K-block counter: the ring never drains between tiles
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN_;
+                for (int kb = 0; kb < nkb; ++kb, ++kbc) {
+                    const int s = kbc % NST;
+                    mbar_wait(&empty[s], ((kbc / NST) & 1) ^ 1);
+                    uint8_t* st = smem + s * STAGE_BYTES;
+                    mbar_expect_tx(&full[s], STAGE_BYTES);
+                    tma_load_2d(st, &tmA, &full[s], kb * BK, m0);                          // A_hi
+                    tma_load_2d(st + A_SUB, &tmA, &full[s], p.Kp + kb * BK, m0);           // A_lo
+                    tma_load_2d(st + 2 * A_SUB, &tmB, &full[s], kb * BK, n0);              // W_hi
+                    tma_load_2d(st + 2 * A_SUB + B_SUB, &tmB, &full[s], p.Kp + kb * BK, n0);  // W_lo
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (single thread) =====================
+        if (lane == 0) {
+            uint32_t kbc = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int ab = it & 1;
+                mbar_wait(&tmem_empty[ab], (((it >> 1) & 1) ^ 1));  // epilogue drained this accumulator (first two: free)
+                tc_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)(ab * BN_);
+                for (int kb = 0; kb < nkb; ++kb, ++kbc) {
+                    const int s = kbc % NST;
+                    mbar_wait(&full[s], (kbc / NST) & 1);
+                    tc_fence_after();
+                    const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+                    const uint64_t a_hi = make_desc<BK>(base), a_lo = make_desc<BK>(base + A_SUB);
+                    const uint64_t w_hi = make_desc<BK>(base + 2 * A_SUB), w_lo = make_desc<BK>(base + 2 * A_SUB + B_SUB);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t ko = (uint64_t)(k * 2);
+                        umma_bf16(d, a_lo + ko, w_hi + ko, IDESC_P, (kb | k) ? 1u : 0u);
+                        umma_bf16(d, a_hi + ko, w_lo + ko, IDESC_P, 1u);
+                        umma_bf16(d, a_hi + ko, w_hi + ko, IDESC_P, 1u);
+                    }
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(&tmem_full[ab]);
+                if (dbg && it < 16) p.dbg[8 + it] = clock64();
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue (overlaps the next tile's main loop) =====================
+        const int q = warp & 3, half = (warp - 4) >> 2;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int ab = it & 1;
+            const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN_;
+            mbar_wait(&tmem_full[ab], (it >> 1) & 1);
+            tc_fence_after();
+            if (dbg && threadIdx.x == 128 && it < 16) p.dbg[40 + it] = clock64();
+            if (MODE == 0) epilogue_tile_coalesced<ACT, BN_>(p, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane, stage_buf + (warp - 4) * (32 * 32));
+            else epilogue_tile_fast<ACT, BN_, MODE>(p, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane, smem_u32(stage_buf + (warp - 4) * (32 * 32)));
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[ab]);
+            if (dbg && threadIdx.x == 128 && it < 16) p.dbg[72 + it] = clock64();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 2 * BN_);
 }
 
 // fp32 [M,K] -> bf16 (hi | lo) [M, 2*Kp], zero padded to Kp
@@ -333,12 +609,12 @@ EncodeTiledFn get_encode() {
 }
 
 // 2-D bf16 tensor [rows, cols] row-major, box = BK cols x 128 rows, swizzle span = BK*2 bytes, OOB -> zeros
-bool make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, int BK) {
+bool make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, int BK, int box_rows = BM) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
     cuuint64_t gdim[2] = {cols, rows};
     cuuint64_t gstride[1] = {cols * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -371,13 +647,66 @@ extern "C" int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp
     AM_REQUIRE(!residual || ldr >= N, AM_EINVAL, "am_linear_tc: bad residual stride");
     AM_REQUIRE((reinterpret_cast<uintptr_t>(A2) & 15u) == 0 && (reinterpret_cast<uintptr_t>(W2) & 15u) == 0 &&
                (!Y2 || (reinterpret_cast<uintptr_t>(Y2) & 15u) == 0), AM_EALIGN, "am_linear_tc: operands must be 16-byte aligned");
-    // kernel variant (tuning knob, read once): "32x3" (default: BK=32, 3 stages, 2 CTAs/SM), "32x6", "64x3" (1 CTA/SM)
+    // kernel variant (tuning knob, read once): default "persistent"; legacy one-tile-per-CTA kernels "32x3" (BK=32, 3 stages,
+    // 2 CTAs/SM), "32x6", "64x3" (1 CTA/SM) are kept for A/B measurements
     static int variant = -1;
     if (variant < 0) {
         const char* e = getenv("AMB200_TC_VARIANT");
-        variant = 0;
+        variant = 3;
+        if (e && !strcmp(e, "32x3")) variant = 0;
         if (e && !strcmp(e, "32x6")) variant = 1;
         if (e && !strcmp(e, "64x3")) variant = 2;
+    }
+    if (variant == 3) {
+        // tile width: 256 when that still gives every SM >= ~2 tiles, else 128 (more, smaller tiles)
+        const int mt = cdiv(M, BM);
+        const bool wide = N >= 256 && (int64_t)mt * cdiv(N, 256) >= 2 * AM_NUM_SMS;
+        const int bn = wide ? 256 : 128;
+        const int nt = cdiv(N, bn), total = mt * nt;
+        CUtensorMap tmA, tmB;
+        AM_REQUIRE(make_map(&tmA, A2, (uint64_t)M, (uint64_t)2 * Kp, 32, BM), AM_ELAUNCH, "am_linear_tc: cuTensorMapEncodeTiled(A) failed");
+        AM_REQUIRE(make_map(&tmB, W2, (uint64_t)N, (uint64_t)2 * Kp, 32, bn), AM_ELAUNCH, "am_linear_tc: cuTensorMapEncodeTiled(W) failed");
+        TcParams p{M, N, Kp, bias, act, residual, ldr, res_mod, Y, ldy, yin_g, yout_g, y_off, reinterpret_cast<__nv_bfloat16*>(Y2), Np2, 0, g_tc_dbg};
+        p.vecY = Y && (reinterpret_cast<uintptr_t>(Y) & 15u) == 0 && (ldy % 4 == 0);
+        const int grid = total < AM_NUM_SMS ? total : AM_NUM_SMS;
+        cudaStream_t st = as_stream(stream);
+#define AM_TCP_LAUNCH(BN_, NST_, ACT_, MODE_)                                                                                   \
+    do {                                                                                                                        \
+        constexpr int smem_ = NST_ * (2 * BM * 32 * 2 + 2 * BN_ * 32 * 2) + 1024 + 256 + 8 * 32 * 32 * 4;                       \
+        static bool attr_ = false;                                                                                              \
+        if (!attr_) {                                                                                                           \
+            if (cudaFuncSetAttribute(gemm_tc_persistent_kernel<BN_, NST_, ACT_, MODE_>,                                         \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem_) != cudaSuccess) {                      \
+                am_set_error_("am_linear_tc: shared memory opt-in failed");                                                     \
+                return AM_ELAUNCH;                                                                                              \
+            }                                                                                                                   \
+            attr_ = true;                                                                                                       \
+        }                                                                                                                       \
+        gemm_tc_persistent_kernel<BN_, NST_, ACT_, MODE_><<<grid, TCP_THREADS, smem_, st>>>(tmA, tmB, p, nt, total);              \
+    } while (0)
+        // epilogue mode: 1 / 2 = specialised fast paths of the big trunk GEMMs, 0 = general
+        const int a15 = act & 15;
+        const bool plain = yin_g == 0 && res_mod == 0 && (N % bn) == 0 && !(act & AM_ACT_AFTER_RES) &&
+                           (!bias || (reinterpret_cast<uintptr_t>(bias) & 7u) == 0);
+        int mode = 0;
+        if (plain && Y2 && !Y && !residual && Np2 == N && (a15 == AM_ACT_NONE || a15 == AM_ACT_GELU)) mode = 1;
+        if (plain && Y && !Y2 && residual && a15 == AM_ACT_NONE && (ldy % 2) == 0 && (ldr % 2) == 0 &&
+            (reinterpret_cast<uintptr_t>(Y) & 7u) == 0 && (reinterpret_cast<uintptr_t>(residual) & 7u) == 0) mode = 2;
+#define AM_TCP_BY_MODE(BN_, NST_)                                                                  \
+    if (mode == 1 && a15 == AM_ACT_GELU) AM_TCP_LAUNCH(BN_, NST_, AM_ACT_GELU, 1);                  \
+    else if (mode == 1) AM_TCP_LAUNCH(BN_, NST_, AM_ACT_NONE, 1);                                   \
+    else if (mode == 2) AM_TCP_LAUNCH(BN_, NST_, AM_ACT_NONE, 2);                                   \
+    else switch (a15) {                                                                            \
+        case AM_ACT_GELU: AM_TCP_LAUNCH(BN_, NST_, AM_ACT_GELU, 0); break;                          \
+        case AM_ACT_SILU: AM_TCP_LAUNCH(BN_, NST_, AM_ACT_SILU, 0); break;                          \
+        case AM_ACT_RELU: AM_TCP_LAUNCH(BN_, NST_, AM_ACT_RELU, 0); break;                          \
+        default: AM_TCP_LAUNCH(BN_, NST_, AM_ACT_NONE, 0); break;                                   \
+    }
+        if (wide) { AM_TCP_BY_MODE(256, 4) } else { AM_TCP_BY_MODE(128, 6) }
+#undef AM_TCP_BY_MODE
+#undef AM_TCP_LAUNCH
+        AM_LAUNCH_CHECK("linear_tc");
+        return AM_OK;
     }
     const int BKsel = variant == 2 ? 64 : 32;
     AM_REQUIRE(Kp % BKsel == 0, AM_EINVAL, "am_linear_tc: Kp must be a multiple of the K block");

@@ -12,15 +12,32 @@ xs, wsp = ops.split_bf16(x, M, K), ops.split_bf16(w, N, K)
 y = torch.empty(M, N, device=dev)
 L = lib.load()
 L.am_tc_set_debug_.argtypes = [ctypes.c_void_p]
+case = os.environ.get("TC_CASE", "plain")
+bias = torch.randn(N, device=dev, generator=g)
+res = torch.randn(M, N, device=dev, generator=g)
+y2 = torch.zeros(M, 2 * N, dtype=torch.bfloat16, device=dev)
+def run():
+    if case == "qkv":      # bias -> bf16 split only (fast mode 1)
+        ops.linear_tc(xs, wsp, M, N, K, y2=y2, bias=bias, Np2=N)
+    elif case == "out":    # bias + residual -> fp32 (fast mode 2)
+        ops.linear_tc(xs, wsp, M, N, K, y=y, bias=bias, residual=res)
+    else:
+        ops.linear_tc(xs, wsp, M, N, K, y=y)
 for _ in range(3):
-    ops.linear_tc(xs, wsp, M, N, K, y=y)
+    run()
 dbg = torch.zeros(256, dtype=torch.int64, device=dev)
+dbg[255] = int(os.environ.get("TC_DFLAGS", "0"))
 L.am_tc_set_debug_(dbg.data_ptr())
-ops.linear_tc(xs, wsp, M, N, K, y=y)
+run()
 torch.cuda.synchronize()
 L.am_tc_set_debug_(None)
 d = dbg.cpu().tolist()
 t0 = d[0]
+if os.environ.get("AMB200_TC_VARIANT", "persistent") == "persistent":
+    print("tile  mma_committed  epi_start  epi_end   (cycles since CTA 0 start)")
+    for it in range(6):
+        print(it, d[8 + it] - t0, d[40 + it] - t0, d[72 + it] - t0)
+    sys.exit(0)
 nkb = K // (64 if os.environ.get("AMB200_TC_VARIANT") == "64x3" else 32)
 print("prologue sync done +", d[1] - t0, " tmem_full seen +", d[2] - t0, " epilogue done +", d[3] - t0, " teardown +", d[4] - t0)
 print("kb  tma_issue  full_seen  mma_issued(commit)")
