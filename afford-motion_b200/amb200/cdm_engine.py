@@ -8,6 +8,7 @@ The Perceiver here has exactly 2 latent tokens (text, time), so both cross-atten
 What remains dense per point is the 256->256 GELU layer (one GEMM over B*N rows).  The latent side (2 tokens per
 sample) is a chain of small GEMM / LayerNorm launches, graph-captured with the rest of the step.
 """
+import os
 from dataclasses import dataclass
 from typing import Dict, Optional
 
@@ -38,6 +39,7 @@ class CDMEngine:
         self._version = None
         self.w: Dict[str, torch.Tensor] = {}
         self._ws = {}
+        self.gemm = os.environ.get("AMB200_GEMM", "tc")  # tcgen05 (default) or fp32 SIMT for the per-point MLP GEMM
 
     def refresh(self):
         v = params_version(self.m)
@@ -127,6 +129,8 @@ class CDMEngine:
         dm_ = cm.decoder_cross_attn[1].module
         w["d_m_g"], w["d_m_b"] = c(dm_[0].weight), c(dm_[0].bias)
         w["d_m1_w"], w["d_m1_b"] = c(dm_[1].weight), c(dm_[1].bias)
+        if self.gemm == "tc":
+            w["d_m1_w2"] = ops.split_bf16(w["d_m1_w"], w["d_m1_w"].shape[0], w["d_m1_w"].shape[1])
         # contact_layer(h1 + W2 g + b2) = [Wc | Wc W2] [h1; g] + (Wc b2 + bc)
         Wc, bc = _d(m.contact_layer.weight), _d(m.contact_layer.bias)
         w["head_w"] = torch.cat([Wc, Wc @ _d(dm_[3].weight)], dim=1).float().contiguous()
@@ -158,7 +162,8 @@ class CDMEngine:
             ws = dict(L0=e(B, 2, DL), LN=e(2 * B, DL), Q=e(2 * B, DL), QF=torch.zeros(B, R, C + 4, device=dev), Z=e(B, R, C),
                       PART=e(B, nchunk, R, C + 2), AO=e(2 * B, DL), La=e(2 * B, DL), Lb=e(2 * B, DL), Hh=e(2 * B, DL),
                       QKV=e(2 * B, 3 * DL), KV=e(2 * B, 2 * C), KF=torch.zeros(B, R, C + 4, device=dev), U=e(B, R, C), H1=e(B * N, C),
-                      HN=e(B * N, C), Gm=e(B * N, C), nchunk=nchunk, cond_id=None)
+                      HN=None if self.gemm == "tc" else e(B * N, C), HN2=torch.zeros(B * N, 2 * C, dtype=torch.bfloat16, device=dev) if self.gemm == "tc" else None,
+                      Gm=e(B * N, C), nchunk=nchunk, cond_id=None)
             self._ws[key] = ws
         return ws
 
@@ -215,8 +220,11 @@ class CDMEngine:
             ops.linear(ws["KV"][:, h * hdd:], w["d_qfold"][h], ws["KF"], M2, C + 1, hdd, ldx=2 * C, ldy=C + 4, ymap=(2, R, 2 * h))
             ops.linear(ws["KV"][:, C + h * hdd:], w["d_o_w"][:, h * hdd:], ws["U"], M2, C, hdd, ldx=2 * C, ldw=C, ymap=(2, R, 2 * h))
         ops.cdm_decoder_point(x, cond.xyz, w["dd_w"], w["dd_b"], w["d_qn_g"], w["d_qn_b"], ws["KF"], C + 4, ws["U"], w["d_o_b"],
-                              w["d_m_g"], w["d_m_b"], ws["H1"], ws["HN"], B, N, cx)
-        ops.linear(ws["HN"], w["d_m1_w"], ws["Gm"], B * N, C, C, bias=w["d_m1_b"], act="gelu")
+                              w["d_m_g"], w["d_m_b"], ws["H1"], ws["HN"], B, N, cx, hn2=ws["HN2"])
+        if self.gemm == "tc":  # the one dense per-point layer: 256 -> 256 GELU on the tensor cores
+            ops.linear_tc(ws["HN2"], w["d_m1_w2"], B * N, C, C, y=ws["Gm"], bias=w["d_m1_b"], act="gelu")
+        else:
+            ops.linear(ws["HN"], w["d_m1_w"], ws["Gm"], B * N, C, C, bias=w["d_m1_b"], act="gelu")
         if out is None:
             out = torch.empty(B, N, self.out_dim, device=dev)
         ops.linear_skinny(ws["H1"], C, ws["Gm"], C, w["head_w"], w["head_b"], out, B * N, self.out_dim)

@@ -38,7 +38,7 @@ _SIGS = {
     "am_transition_down_fwd": (c_int, [P] * 7 + [I, I, I, I, P]),
     "am_cdm_encoder_partial": (c_int, [P, P, P, P, P, P, P, I, P, I, I, I, I, P]),
     "am_cdm_encoder_combine": (c_int, [P, P, I, I, P]),
-    "am_cdm_decoder_point": (c_int, [P, P, P, P, P, P, P, I, P, P, P, P, P, P, I, I, I, P]),
+    "am_cdm_decoder_point": (c_int, [P, P, P, P, P, P, P, I, P, P, P, P, P, P, P, I, I, I, P]),
     "am_linear_skinny": (c_int, [P, I, I, P, I, I, P, P, P, I, I, I, P]),
     "am_mha_tc_fwd": (c_int, [P, P, P, P, I, I, I, I, c_float, P]),
     "am_split_bf16": (c_int, [P, I, P, I, I, I, P]),

@@ -162,9 +162,9 @@ def cdm_encoder_combine(part, z, B, nchunk):
     _l.check(_l.load().am_cdm_encoder_combine(_ptr(part), _ptr(z), B, nchunk, _stream()), "am_cdm_encoder_combine")
 
 
-def cdm_decoder_point(x_t, xyz, wd, bd, lnq_g, lnq_b, kf, ldk, U, bo, lnm_g, lnm_b, h1, hn, B, N, cx):
+def cdm_decoder_point(x_t, xyz, wd, bd, lnq_g, lnq_b, kf, ldk, U, bo, lnm_g, lnm_b, h1, hn, B, N, cx, hn2=None):
     _l.check(_l.load().am_cdm_decoder_point(_ptr(x_t), _ptr(xyz), _ptr(wd), _ptr(bd), _ptr(lnq_g), _ptr(lnq_b), _ptr(kf), ldk, _ptr(U),
-                                           _ptr(bo), _ptr(lnm_g), _ptr(lnm_b), _ptr(h1), _ptr(hn), B, N, cx, _stream()),
+                                           _ptr(bo), _ptr(lnm_g), _ptr(lnm_b), _ptr(h1), _ptr(hn), _ptr(hn2), B, N, cx, _stream()),
              "am_cdm_decoder_point")
 
 

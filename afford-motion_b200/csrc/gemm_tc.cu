@@ -310,7 +310,8 @@ __device__ __forceinline__ void epilogue_tile_coalesced(const TcParams& p, uint3
 }
 
 // Fast-path epilogue (the four big CMDM GEMMs): no row map, no broadcast residual, tile entirely inside N, even strides.
-// MODE 1: bias (+act) -> bf16 (hi|lo) only (in_proj, FFN1);  MODE 2: bias + fp32 residual -> fp32 only (out_proj, FFN2).
+// MODE 1: bias (+act) -> bf16 (hi|lo) only (in_proj, FFN1);  MODE 2: bias (+act) (+ fp32 residual) -> fp32 only (out_proj, FFN2,
+// CDM per-point MLP).
 // Everything that is loop-invariant is hoisted and all 16 shared / residual loads of a 32x32 block are issued before the
 // first dependent instruction, so the two epilogue warps of a scheduler keep several memory operations in flight.
 template <int ACT, int NCOLS, int MODE>
@@ -351,7 +352,7 @@ __device__ __forceinline__ void epilogue_tile_fast(const TcParams& p, uint32_t t
             for (int i = 0; i < 16; ++i) {
                 const int r = 2 * i + rsel;
                 rv[i] = make_float2(0.f, 0.f);
-                if (r < rows_valid) rv[i] = *reinterpret_cast<const float2*>(p.residual + (int64_t)(m_base + r) * p.ldr + n);
+                if (p.residual && r < rows_valid) rv[i] = *reinterpret_cast<const float2*>(p.residual + (int64_t)(m_base + r) * p.ldr + n);
             }
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -690,11 +691,12 @@ extern "C" int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp
                            (!bias || (reinterpret_cast<uintptr_t>(bias) & 7u) == 0);
         int mode = 0;
         if (plain && Y2 && !Y && !residual && Np2 == N && (a15 == AM_ACT_NONE || a15 == AM_ACT_GELU)) mode = 1;
-        if (plain && Y && !Y2 && residual && a15 == AM_ACT_NONE && (ldy % 2) == 0 && (ldr % 2) == 0 &&
-            (reinterpret_cast<uintptr_t>(Y) & 7u) == 0 && (reinterpret_cast<uintptr_t>(residual) & 7u) == 0) mode = 2;
+        if (plain && Y && !Y2 && (a15 == AM_ACT_NONE || a15 == AM_ACT_GELU) && (ldy % 2) == 0 && (reinterpret_cast<uintptr_t>(Y) & 7u) == 0 &&
+            (!residual || ((ldr % 2) == 0 && (reinterpret_cast<uintptr_t>(residual) & 7u) == 0))) mode = 2;
 #define AM_TCP_BY_MODE(BN_, NST_)                                                                  \
     if (mode == 1 && a15 == AM_ACT_GELU) AM_TCP_LAUNCH(BN_, NST_, AM_ACT_GELU, 1);                  \
     else if (mode == 1) AM_TCP_LAUNCH(BN_, NST_, AM_ACT_NONE, 1);                                   \
+    else if (mode == 2 && a15 == AM_ACT_GELU) AM_TCP_LAUNCH(BN_, NST_, AM_ACT_GELU, 2);             \
     else if (mode == 2) AM_TCP_LAUNCH(BN_, NST_, AM_ACT_NONE, 2);                                   \
     else switch (a15) {                                                                            \
         case AM_ACT_GELU: AM_TCP_LAUNCH(BN_, NST_, AM_ACT_GELU, 0); break;                          \

@@ -3,6 +3,7 @@
 //   score = (W_k^T q).LN(e) + q.b_k     and     sum_j p_j (W_v LN(e_j) + b_v) = W_v (sum_j p_j LN(e_j)) + b_v
 // so K/V [B,N,512] are never formed; each point costs O(16*256) instead of O(256*1024) MACs.
 // One warp per point, 8 channels per lane (C = 256), fp32 throughout, flash-style (max,sum,acc) partials.
+#include <cuda_bf16.h>
 #include <math_constants.h>
 #include "common.cuh"
 
@@ -146,7 +147,7 @@ cdm_decoder_point_kernel(const float* __restrict__ x_t, const float* __restrict_
                          const float* __restrict__ bd, const float* __restrict__ lnq_g, const float* __restrict__ lnq_b,
                          const float* __restrict__ kf, int ldk, const float* __restrict__ U, const float* __restrict__ bo,
                          const float* __restrict__ lnm_g, const float* __restrict__ lnm_b, float* __restrict__ h1,
-                         float* __restrict__ hn, int N, int cx, int pts_per_cta) {
+                         float* __restrict__ hn, __nv_bfloat16* __restrict__ hn2, int N, int cx, int pts_per_cta) {
     extern __shared__ __align__(16) float sm[];
     const int cin = cx + 3;
     float* Wt = sm;                  // [cin][C]
@@ -200,9 +201,24 @@ cdm_decoder_point_kernel(const float* __restrict__ x_t, const float* __restrict_
         reinterpret_cast<float4*>(h1p)[0] = make_float4(o[0], o[1], o[2], o[3]);
         reinterpret_cast<float4*>(h1p)[1] = make_float4(o[4], o[5], o[6], o[7]);
         layernorm8(o, lnm_g, lnm_b, lane);
-        float* hnp = hn + ((int64_t)b * N + j) * C + lane * CL;
-        reinterpret_cast<float4*>(hnp)[0] = make_float4(o[0], o[1], o[2], o[3]);
-        reinterpret_cast<float4*>(hnp)[1] = make_float4(o[4], o[5], o[6], o[7]);
+        if (hn) {
+            float* hnp = hn + ((int64_t)b * N + j) * C + lane * CL;
+            reinterpret_cast<float4*>(hnp)[0] = make_float4(o[0], o[1], o[2], o[3]);
+            reinterpret_cast<float4*>(hnp)[1] = make_float4(o[4], o[5], o[6], o[7]);
+        }
+        if (hn2) {  // bf16 (hi | lo) operand of the tcgen05 MLP GEMM, row stride 2*C
+            uint32_t wh[4], wl[4];
+#pragma unroll
+            for (int i = 0; i < CL; i += 2) {
+                __nv_bfloat16 h0 = __float2bfloat16_rn(o[i]), h1 = __float2bfloat16_rn(o[i + 1]);
+                __nv_bfloat16 l0 = __float2bfloat16_rn(o[i] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(o[i + 1] - __bfloat162float(h1));
+                wh[i / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                wl[i / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            }
+            __nv_bfloat16* base2 = hn2 + ((int64_t)b * N + j) * (2 * C) + lane * CL;
+            *reinterpret_cast<uint4*>(base2) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+            *reinterpret_cast<uint4*>(base2 + C) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+        }
     }
 }
 
@@ -272,8 +288,8 @@ extern "C" int am_cdm_encoder_combine(const float* part, float* z, int B, int nc
 
 extern "C" int am_cdm_decoder_point(const float* x_t, const float* xyz, const float* wd, const float* bd, const float* lnq_g,
                                     const float* lnq_b, const float* kf, int ldk, const float* U, const float* bo, const float* lnm_g,
-                                    const float* lnm_b, float* h1, float* hn, int B, int N, int cx, am_stream_t stream) {
-    AM_REQUIRE(x_t && xyz && wd && bd && lnq_g && lnq_b && kf && U && bo && lnm_g && lnm_b && h1 && hn, AM_EINVAL,
+                                    const float* lnm_b, float* h1, float* hn, void* hn2, int B, int N, int cx, am_stream_t stream) {
+    AM_REQUIRE(x_t && xyz && wd && bd && lnq_g && lnq_b && kf && U && bo && lnm_g && lnm_b && h1 && (hn || hn2), AM_EINVAL,
                "am_cdm_decoder_point: null pointer");
     AM_REQUIRE(B > 0 && N > 0 && cx > 0 && cx + 3 <= MAXCIN && ldk >= C + 1, AM_EINVAL, "am_cdm_decoder_point: bad dims");
     size_t smem = sizeof(float) * ((size_t)(cx + 3) * C + (size_t)R * (C + 4) + (size_t)R * C);
@@ -283,7 +299,7 @@ extern "C" int am_cdm_decoder_point(const float* x_t, const float* xyz, const fl
     int pts = 64;
     while ((int64_t)cdiv(N, pts) * B > 148 * 8 && pts < 1024) pts *= 2;
     cdm_decoder_point_kernel<<<dim3(cdiv(N, pts), B), PW * 32, smem, as_stream(stream)>>>(x_t, xyz, wd, bd, lnq_g, lnq_b, kf, ldk, U, bo,
-                                                                                          lnm_g, lnm_b, h1, hn, N, cx, pts);
+                                                                                          lnm_g, lnm_b, h1, hn, reinterpret_cast<__nv_bfloat16*>(hn2), N, cx, pts);
     AM_LAUNCH_CHECK("cdm_decoder_point");
     return AM_OK;
 }

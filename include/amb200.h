@@ -162,8 +162,9 @@ int am_cdm_encoder_combine(const float* part, float* z, int B, int nchunk, am_st
  *   out h1 [B*N,256] and hn = LN_m(h1) [B*N,256] */
 int am_cdm_decoder_point(const float* x_t, const float* xyz, const float* wd, const float* bd, const float* lnq_g,
                          const float* lnq_b, const float* kf, int ldk, const float* U, const float* bo,
-                         const float* lnm_g, const float* lnm_b, float* h1, float* hn, int B, int N, int cx,
+                         const float* lnm_g, const float* lnm_b, float* h1, float* hn, void* hn2, int B, int N, int cx,
                          am_stream_t stream);
+/* (hn2 != NULL: hn also as bf16 (hi|lo) [B*N, 512] for am_linear_tc; hn may then be NULL) */
 
 /* Y[M, N<=8] = X1 W[:, :K1]^T + X2 W[:, K1:]^T + bias.  Used for the CDM output head with the second MLP
  * linear folded in: contact_layer(h1 + W2 g + b2) = [Wc | Wc W2] [h1 ; g] + (Wc b2 + bc)  (cdm.py:472,511). */
