@@ -15,16 +15,17 @@ g = torch.Generator(device=dev).manual_seed(0)
 r = lambda *s: torch.randn(*s, device=dev, generator=g)
 x, win, wout, w1, w2 = r(M, D), r(3 * D, D) / 22, r(D, D) / 22, r(FF, D) / 22, r(D, FF) / 32
 xs, wins, wouts, w1s, w2s = (ops.split_bf16(t, t.shape[0], t.shape[1]) for t in (x, win, wout, w1, w2))
-qkv, tmp, y1 = torch.empty(M, 3 * D, device=dev), torch.empty(M, D, device=dev), torch.empty(M, D, device=dev)
+qkvs = torch.zeros(M, 6 * D, dtype=torch.bfloat16, device=dev)
+tmp, y1 = torch.empty(M, D, device=dev), torch.empty(M, D, device=dev)
 ffs = torch.zeros(M, 2 * FF, dtype=torch.bfloat16, device=dev)
 atts, y1s = torch.zeros(M, 2 * D, dtype=torch.bfloat16, device=dev), torch.zeros(M, 2 * D, dtype=torch.bfloat16, device=dev)
 bias3, bias1, biasf = r(3 * D), r(D), r(FF)
 gam, bet = r(D), r(D)
 pad = torch.zeros(B, S, dtype=torch.uint8, device=dev)
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
-for _ in range(reps):
-    ops.linear_tc(xs, wins, M, 3 * D, D, y=qkv, bias=bias3)                              # QKV
-    ops.mha_fwd(qkv, None, pad, B, S, H, 64, 0.125, out2=atts)                          # attention
+for _ in range(reps):   # exactly the per-layer sequence of amb200.cmdm_engine._forward_tc
+    ops.linear_tc(xs, wins, M, 3 * D, D, y2=qkvs, bias=bias3, Np2=3 * D)                 # in_proj -> bf16 (hi|lo) QKV
+    ops.mha_tc_fwd(qkvs, None, atts, pad, B, S, H, 64, 0.125)                           # tcgen05 attention
     ops.linear_tc(atts, wouts, M, D, D, y=tmp, bias=bias1, residual=x)                  # out_proj + residual
     ops.layernorm(tmp, gam, bet, y1, M, D, y2=y1s)                                      # LN1
     ops.linear_tc(y1s, w1s, M, FF, D, y2=ffs, bias=biasf, act="gelu", Np2=FF)           # FFN1 + GELU (split out only)
