@@ -1,0 +1,410 @@
+"""torch.autograd Functions whose forward AND backward are libamb200 kernels — the training path of the CMDM denoiser
+(SURVEY §8 a10/a28/a29).  torch supplies only the tape, parameter storage and data movement (cat / slice / view);
+every arithmetic op below runs a kernel from csrc/train_kernels.cu (fp32 SIMT; tensor-core versions are next)."""
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+from torch.autograd import Function
+
+from . import lib as _l
+from . import ops as _ops
+
+_L = None
+
+
+def L():
+    global _L
+    if _L is None:
+        _L = _l.load()
+    return _L
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def gemm(A, B, C, M, N, K, transA=False, transB=False, alpha=1.0, beta=0.0, lda=None, ldb=None, ldc=None, batch=1, bdiv=1,
+         sA=(0, 0), sB=(0, 0), sC=(0, 0)):
+    lda = (M if transA else K) if lda is None else lda
+    ldb = (K if transB else N) if ldb is None else ldb
+    ldc = N if ldc is None else ldc
+    _l.check(L().am_gemm_f32(int(transA), int(transB), M, N, K, float(alpha), _p(A), lda, _p(B), ldb, float(beta), _p(C), ldc, batch, bdiv,
+                             sA[0], sA[1], sB[0], sB[1], sC[0], sC[1], _st()), "am_gemm_f32")
+    return C
+
+
+class LinearFn(Function):
+    """y = x W^T (+ b) on the last dim; x [..., K], W [N, K]."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x2 = _c(x).view(-1, x.shape[-1])
+        w = _c(w)
+        M, K = x2.shape
+        N = w.shape[0]
+        y = torch.empty(M, N, device=x.device)
+        _ops.linear(x2, w, y, M, N, K, bias=None if b is None else _c(b))  # fp32 SIMT GEMM with the bias fused in the epilogue
+        ctx.save_for_backward(x2, w)
+        ctx.has_bias = b is not None
+        ctx.xshape = x.shape
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w = ctx.saved_tensors
+        M, K = x2.shape
+        N = w.shape[0]
+        dy2 = _c(dy).view(M, N)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(M, K, device=dy.device)
+            gemm(dy2, w, dx, M, K, N)  # dX = dY W
+            dx = dx.view(ctx.xshape)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty(N, K, device=dy.device)
+            gemm(dy2, x2, dw, N, K, M, transA=True)  # dW = dY^T X
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = torch.empty(N, device=dy.device)
+            _l.check(L().am_colsum_f32(_p(dy2), N, _p(db), M, N, 0.0, _st()), "am_colsum_f32")
+        return dx, dw, db
+
+
+def _unary(fwd, bwd, name):
+    class Fn(Function):
+        @staticmethod
+        def forward(ctx, x):
+            x = _c(x)
+            y = torch.empty_like(x)
+            _l.check(getattr(L(), fwd)(_p(x), _p(y), x.numel(), _st()), fwd)
+            ctx.save_for_backward(x)
+            return y
+
+        @staticmethod
+        def backward(ctx, dy):
+            (x,) = ctx.saved_tensors
+            dy = _c(dy)
+            dx = torch.empty_like(x)
+            _l.check(getattr(L(), bwd)(_p(dy), _p(x), _p(dx), x.numel(), _st()), bwd)
+            return dx
+    Fn.__name__ = name
+    return Fn
+
+
+GeluFn = _unary("am_gelu_fwd", "am_gelu_bwd", "GeluFn")
+SiluFn = _unary("am_silu_fwd", "am_silu_bwd", "SiluFn")
+
+
+class AddFn(Function):
+    """y = a + b (optionally ReLU), same shapes."""
+
+    @staticmethod
+    def forward(ctx, a, b, relu):
+        a, b = _c(a), _c(b)
+        y = torch.empty_like(a)
+        _l.check(L().am_add_f32(_p(a), _p(b), _p(y), a.numel(), int(relu), _st()), "am_add_f32")
+        ctx.relu = relu
+        if relu:
+            ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _c(dy)
+        if ctx.relu:
+            (y,) = ctx.saved_tensors
+            d = torch.empty_like(dy)
+            _l.check(L().am_relu_bwd(_p(dy), _p(y), _p(d), dy.numel(), _st()), "am_relu_bwd")
+            dy = d
+        return dy, dy, None
+
+
+class DropoutFn(Function):
+    @staticmethod
+    def forward(ctx, x, p, seed, site):
+        if p <= 0.0:
+            ctx.p = 0.0
+            return x
+        x = _c(x)
+        y = torch.empty_like(x)
+        _l.check(L().am_dropout(_p(x), _p(y), x.numel(), float(p), seed, site, _st()), "am_dropout")
+        ctx.p, ctx.seed, ctx.site = p, seed, site
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        if ctx.p <= 0.0:
+            return dy, None, None, None
+        dy = _c(dy)
+        dx = torch.empty_like(dy)
+        _l.check(L().am_dropout(_p(dy), _p(dx), dy.numel(), float(ctx.p), ctx.seed, ctx.site, _st()), "am_dropout")
+        return dx, None, None, None
+
+
+class LayerNormFn(Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        x2 = _c(x).view(-1, x.shape[-1])
+        M, D = x2.shape
+        y = torch.empty_like(x2)
+        _l.check(L().am_layernorm(_p(x2), D, None, D, _p(gamma), _p(beta), _p(y), D, M, D, float(eps), None, 0, _st()), "am_layernorm")
+        ctx.save_for_backward(x2, gamma)
+        ctx.eps, ctx.shape = eps, x.shape
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, gamma = ctx.saved_tensors
+        M, D = x2.shape
+        dy2 = _c(dy).view(M, D)
+        dx = torch.empty_like(x2)
+        dg, db = torch.zeros(D, device=dy.device), torch.zeros(D, device=dy.device)
+        _l.check(L().am_layernorm_bwd(_p(dy2), _p(x2), None, _p(gamma), _p(dx), _p(dg), _p(db), M, D, float(ctx.eps), _st()), "am_layernorm_bwd")
+        return dx.view(ctx.shape), dg, db, None
+
+
+class AttentionFn(Function):
+    """softmax(q k^T * scale + key mask) (dropout) v on packed qkv [B,S,3*H*hd] -> [B,S,H*hd]; the probabilities are kept
+    for the backward pass (training only; sampling uses the tcgen05 kernel)."""
+
+    @staticmethod
+    def forward(ctx, qkv, key_pad_u8, H, p_drop, seed, site):
+        qkv = _c(qkv)
+        B, S, D3 = qkv.shape
+        D = D3 // 3
+        hd = D // H
+        scale = hd ** -0.5
+        P = torch.empty(B * H, S, S, device=qkv.device)
+        sq = (S * D3, hd)
+        gemm(qkv, qkv[:, :, D:], P, S, S, hd, transB=True, lda=D3, ldb=D3, ldc=S, batch=B * H, bdiv=H, sA=sq, sB=sq, sC=(H * S * S, S * S))
+        _l.check(L().am_softmax_rows_fwd(_p(P), _p(key_pad_u8), B * H * S, S, H * S, float(scale), _st()), "am_softmax_rows_fwd")
+        Pd = P
+        if p_drop > 0:
+            Pd = torch.empty_like(P)
+            _l.check(L().am_dropout(_p(P), _p(Pd), P.numel(), float(p_drop), seed, site, _st()), "am_dropout")
+        out = torch.empty(B, S, D, device=qkv.device)
+        gemm(Pd, qkv[:, :, 2 * D:], out, S, hd, S, lda=S, ldb=D3, ldc=D, batch=B * H, bdiv=H, sA=(H * S * S, S * S), sB=sq, sC=(S * D, hd))
+        ctx.save_for_backward(qkv, P, Pd)
+        ctx.meta = (B, S, D, H, hd, scale, p_drop, seed, site)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, P, Pd = ctx.saved_tensors
+        B, S, D, H, hd, scale, p_drop, seed, site = ctx.meta
+        D3 = 3 * D
+        dout = _c(dout)
+        dqkv = torch.zeros_like(qkv)
+        sq, so, sp = (S * D3, hd), (S * D, hd), (H * S * S, S * S)
+        dP = torch.empty_like(P)
+        gemm(dout, qkv[:, :, 2 * D:], dP, S, S, hd, transB=True, lda=D, ldb=D3, ldc=S, batch=B * H, bdiv=H, sA=so, sB=sq, sC=sp)  # dO V^T
+        gemm(Pd, dout, dqkv[:, :, 2 * D:], S, hd, S, transA=True, lda=S, ldb=D, ldc=D3, batch=B * H, bdiv=H, sA=sp, sB=so, sC=sq)  # dV = Pd^T dO
+        if p_drop > 0:
+            d2 = torch.empty_like(dP)
+            _l.check(L().am_dropout(_p(dP), _p(d2), dP.numel(), float(p_drop), seed, site, _st()), "am_dropout")
+            dP = d2
+        _l.check(L().am_softmax_rows_bwd(_p(dP), _p(P), B * H * S, S, float(scale), _st()), "am_softmax_rows_bwd")  # dS (scaled)
+        gemm(dP, qkv[:, :, D:], dqkv, S, hd, S, lda=S, ldb=D3, ldc=D3, batch=B * H, bdiv=H, sA=sp, sB=sq, sC=sq)  # dQ = dS K
+        gemm(dP, qkv, dqkv[:, :, D:], S, hd, S, transA=True, lda=S, ldb=D3, ldc=D3, batch=B * H, bdiv=H, sA=sp, sB=sq, sC=sq)  # dK = dS^T Q
+        return dqkv, None, None, None, None, None
+
+
+class BatchNormTrainFn(Function):
+    """BatchNorm1d (training: batch statistics over the rows of x [M,C]) with optional fused ReLU.  Under
+    torch.distributed + SyncBatchNorm the (sum, sumsq) / (dbeta, dgamma) accumulators are all-reduced (train_ddp.py:63)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, bn, relu):
+        x = _c(x)
+        M, C = x.shape
+        dev = x.device
+        sync = isinstance(bn, torch.nn.SyncBatchNorm) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        acc = torch.zeros(2 * C, dtype=torch.float64, device=dev)
+        mean, invstd, var = (torch.empty(C, device=dev) for _ in range(3))
+        Mtot = M
+        if sync:
+            # global statistics: sum / sumsq over all ranks, then finalize with the global count
+            _l.check(L().am_bn_train_stats(_p(x), M, C, float(bn.eps), _p(acc), _p(mean), _p(invstd), _p(var), _st()), "am_bn_train_stats")
+            cnt = torch.tensor([float(M)], dtype=torch.float64, device=dev)
+            dist.all_reduce(acc)
+            dist.all_reduce(cnt)
+            Mtot = int(cnt.item())
+            mu = acc[:C] / Mtot
+            v = (acc[C:] / Mtot - mu * mu).clamp_min(0)
+            mean, var, invstd = mu.float(), v.float(), (1.0 / torch.sqrt(v + bn.eps)).float()
+        else:
+            _l.check(L().am_bn_train_stats(_p(x), M, C, float(bn.eps), _p(acc), _p(mean), _p(invstd), _p(var), _st()), "am_bn_train_stats")
+        y = torch.empty_like(x)
+        _l.check(L().am_bn_apply(_p(x), _p(mean), _p(invstd), _p(gamma), _p(beta), _p(y), M, C, int(relu), _st()), "am_bn_apply")
+        if bn.track_running_stats and bn.running_mean is not None:  # torch semantics: unbiased variance, momentum update
+            with torch.no_grad():
+                mom = bn.momentum if bn.momentum is not None else 0.1
+                bn.running_mean.mul_(1 - mom).add_(mean, alpha=mom)
+                bn.running_var.mul_(1 - mom).add_(var * (Mtot / max(Mtot - 1, 1)), alpha=mom)
+                bn.num_batches_tracked += 1
+        ctx.save_for_backward(x, y if relu else x, mean, invstd, gamma)
+        ctx.relu, ctx.sync, ctx.Mtot = relu, sync, Mtot
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, mean, invstd, gamma = ctx.saved_tensors
+        M, C = x.shape
+        dy = _c(dy)
+        acc = torch.zeros(2 * C, dtype=torch.float64, device=dy.device)
+        dx = torch.empty_like(x)
+        dg, db = torch.zeros(C, device=dy.device), torch.zeros(C, device=dy.device)
+        if not ctx.sync:
+            _l.check(L().am_bn_bwd(_p(dy), _p(x), _p(y), _p(mean), _p(invstd), _p(gamma), _p(acc), _p(dx), _p(dg), _p(db), M, C, int(ctx.relu), _st()),
+                     "am_bn_bwd")
+        else:
+            raise NotImplementedError("SyncBatchNorm backward over ranks: next step (needs the reduce / apply halves of am_bn_bwd split)")
+        return dx, dg, db, None, None
+
+
+class GroupCatFn(Function):
+    """G = cat(rel, x[idx]) for TransitionDown (pointtransformer.py:63); gradient flows to x by scatter-add."""
+
+    @staticmethod
+    def forward(ctx, rel, x, idx):
+        x = _c(x)
+        mk, c = idx.numel(), x.shape[1]
+        G = torch.empty(mk, 3 + c, device=x.device)
+        _l.check(L().am_group_cat(_p(rel), _p(x), _p(idx), _p(G), mk, c, _st()), "am_group_cat")
+        ctx.save_for_backward(idx)
+        ctx.n, ctx.c = x.shape[0], c
+        return G
+
+    @staticmethod
+    def backward(ctx, dG):
+        (idx,) = ctx.saved_tensors
+        dG = _c(dG)
+        dx = torch.zeros(ctx.n, ctx.c, device=dG.device)
+        _l.check(L().am_scatter_add_rows(_p(dG), 3 + ctx.c, 3, _p(idx), _p(dx), idx.numel(), ctx.c, _st()), "am_scatter_add_rows")
+        return None, dx, None
+
+
+class MaxPoolKFn(Function):
+    @staticmethod
+    def forward(ctx, Z, m, k):
+        Z = _c(Z)
+        c = Z.shape[1]
+        out = torch.empty(m, c, device=Z.device)
+        arg = torch.empty(m, c, dtype=torch.int32, device=Z.device)
+        _l.check(L().am_maxpool_k_fwd(_p(Z), _p(out), _p(arg), m, k, c, _st()), "am_maxpool_k_fwd")
+        ctx.save_for_backward(arg)
+        ctx.meta = (m, k, c)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (arg,) = ctx.saved_tensors
+        m, k, c = ctx.meta
+        dZ = torch.empty(m * k, c, device=dout.device)
+        _l.check(L().am_maxpool_k_bwd(_p(_c(dout)), _p(arg), _p(dZ), m, k, c, _st()), "am_maxpool_k_bwd")
+        return dZ, None, None
+
+
+class PtWFn(Function):
+    """w = k[idx] - q + pr  (pointtransformer.py:33)."""
+
+    @staticmethod
+    def forward(ctx, qkv, pr, idx, k):
+        qkv, pr = _c(qkv), _c(pr)
+        n, c = qkv.shape[0], qkv.shape[1] // 3
+        w = torch.empty(n * k, c, device=qkv.device)
+        _l.check(L().am_pt_w_fwd(_p(qkv), _p(idx), _p(pr), _p(w), n, k, c, _st()), "am_pt_w_fwd")
+        ctx.save_for_backward(idx)
+        ctx.meta = (n, k, c)
+        return w
+
+    @staticmethod
+    def backward(ctx, dw):
+        (idx,) = ctx.saved_tensors
+        n, k, c = ctx.meta
+        dw = _c(dw)
+        dqkv = torch.zeros(n, 3 * c, device=dw.device)
+        dpr = torch.zeros(n * k, c, device=dw.device)
+        _l.check(L().am_pt_w_bwd(_p(dw), _p(idx), _p(dqkv), _p(dpr), n, k, c, _st()), "am_pt_w_bwd")
+        return dqkv, dpr, None, None
+
+
+class SoftmaxKFn(Function):
+    @staticmethod
+    def forward(ctx, w, n, k):
+        w = _c(w).clone()
+        c8 = w.shape[1]
+        _l.check(L().am_softmax_k_fwd(_p(w), n, k, c8, _st()), "am_softmax_k_fwd")
+        ctx.save_for_backward(w)
+        ctx.meta = (n, k, c8)
+        return w
+
+    @staticmethod
+    def backward(ctx, dw):
+        (w,) = ctx.saved_tensors
+        n, k, c8 = ctx.meta
+        d = _c(dw).clone()
+        _l.check(L().am_softmax_k_bwd(_p(d), _p(w), n, k, c8, _st()), "am_softmax_k_bwd")
+        return d, None, None
+
+
+class PtAggFn(Function):
+    """out[i, ch] = sum_j (v[idx[i,j], ch] + pr[i,j,ch]) * ws[i,j, ch % c8]  (pointtransformer.py:36-37)."""
+
+    @staticmethod
+    def forward(ctx, qkv, pr, ws, idx, k):
+        qkv, pr, ws = _c(qkv), _c(pr), _c(ws)
+        n, c = qkv.shape[0], qkv.shape[1] // 3
+        out = torch.empty(n, c, device=qkv.device)
+        _l.check(L().am_pt_agg_fwd(_p(qkv), _p(idx), _p(pr), _p(ws), _p(out), n, k, c, _st()), "am_pt_agg_fwd")
+        ctx.save_for_backward(qkv, pr, ws, idx)
+        ctx.meta = (n, k, c)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, pr, ws, idx = ctx.saved_tensors
+        n, k, c = ctx.meta
+        dqkv = torch.zeros_like(qkv)
+        dpr = torch.empty_like(pr)
+        dws = torch.empty_like(ws)
+        _l.check(L().am_pt_agg_bwd(_p(_c(dout)), _p(qkv), _p(idx), _p(pr), _p(ws), _p(dqkv), _p(dpr), _p(dws), n, k, c, _st()), "am_pt_agg_bwd")
+        return dqkv, dpr, dws, None, None
+
+
+class MaskedMSEFn(Function):
+    """loss[b] of gaussian_diffusion.py:815-818 (differentiable w.r.t. the model output)."""
+
+    @staticmethod
+    def forward(ctx, pred, target, mask_u8):
+        pred, target = _c(pred), _c(target)
+        B, T, D = pred.shape
+        loss = torch.empty(B, device=pred.device)
+        _l.check(L().am_masked_mse(_p(target), _p(pred), _p(mask_u8), _p(loss), B, T, D, _st()), "am_masked_mse")
+        ctx.save_for_backward(pred, target, mask_u8)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        pred, target, mask = ctx.saved_tensors
+        B, T, D = pred.shape
+        d = torch.empty_like(pred)
+        _l.check(L().am_masked_mse_bwd(_p(target), _p(pred), _p(mask), _p(_c(gloss)), _p(d), B, T, D, _st()), "am_masked_mse_bwd")
+        return d, None, None
+
+
+# ---- functional helpers
+def linear(x, w, b=None):
+    return LinearFn.apply(x, w, b)
+
+
+def bn_train(x, bn, relu=False):
+    return BatchNormTrainFn.apply(x, bn.weight, bn.bias, bn, relu)

@@ -14,36 +14,26 @@ REPO_ROOT = os.path.dirname(PKG_ROOT)
 LIB_PATH = os.path.join(PKG_ROOT, "csrc", "libamb200.so")
 HEADER_PATH = os.path.join(REPO_ROOT, "include", "amb200.h")
 
-P = c_void_p
-I = c_int
-_SIGS = {
-    "am_version": (c_int, []),
-    "am_check_device": (c_int, []),
-    "am_launch_count": (c_int64, []),
-    "am_last_error": (c_char_p, []),
-    "am_randn": (c_int, [P, c_int64, I, c_int64, c_uint64, c_uint64, P]),
-    "am_p_sample_update": (c_int, [P, P, P, P, P, P, P, P, I, I, c_int64, c_uint64, c_int64, P]),
-    "am_ddim_update": (c_int, [P, P, P, P, P, P, P, P, c_float, P, I, I, c_int64, c_uint64, c_int64, P]),
-    "am_q_sample": (c_int, [P, P, P, P, P, P, I, c_int64, P]),
-    "am_masked_mse": (c_int, [P, P, P, P, I, I, I, P]),
-    "am_add_i32": (c_int, [P, c_int32, I, P]),
-    "am_linear_f32": (c_int, [P, I, P, I, P, I, I, I, I, P, I, P, I, I, I, I, I, I, I, I, P]),
-    "am_layernorm": (c_int, [P, I, P, I, P, P, P, I, I, I, c_float, P, I, P]),
-    "am_mha_fwd": (c_int, [P, P, P, I, I, I, I, c_float, P, P]),
-    "am_gather_time_token": (c_int, [P, I, I, I, P, P, I, I, P, P]),
-    "am_gather_rows": (c_int, [P, P, P, I, I, P]),
-    "am_furthestsampling": (c_int, [I, I, P, P, P, P, P, P]),
-    "am_knnquery": (c_int, [I, I, I, P, P, P, P, P, P, P]),
-    "am_pt_layer_fwd": (c_int, [P] * 16 + [I, I, I, P]),
-    "am_transition_down_fwd": (c_int, [P] * 7 + [I, I, I, I, P]),
-    "am_cdm_encoder_partial": (c_int, [P, P, P, P, P, P, P, I, P, I, I, I, I, P]),
-    "am_cdm_encoder_combine": (c_int, [P, P, I, I, P]),
-    "am_cdm_decoder_point": (c_int, [P, P, P, P, P, P, P, I, P, P, P, P, P, P, P, I, I, I, P]),
-    "am_linear_skinny": (c_int, [P, I, I, P, I, I, P, P, P, I, I, I, P]),
-    "am_mha_tc_fwd": (c_int, [P, P, P, P, I, I, I, I, c_float, P]),
-    "am_split_bf16": (c_int, [P, I, P, I, I, I, P]),
-    "am_linear_tc": (c_int, [P, P, I, I, I, P, I, P, I, I, P, I, I, I, I, P, I, P]),
-}
+_CT = {"int": c_int, "int32_t": c_int32, "int64_t": c_int64, "uint64_t": c_uint64, "uint32_t": ctypes.c_uint32, "float": c_float,
+       "am_stream_t": c_void_p}
+
+
+def _parse_header():
+    """ctypes signatures straight from the prototypes in include/amb200.h, so the binding cannot drift from the boundary."""
+    txt = re.sub(r"/\*.*?\*/", "", open(HEADER_PATH).read(), flags=re.S)
+    sigs = {}
+    for ret, name, args in re.findall(r"\b(int64_t|int|const char\*|void)\s+(am_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", txt, flags=re.S):
+        argt = []
+        for a in [x.strip() for x in args.split(",") if x.strip() and x.strip() != "void"]:
+            if "*" in a:
+                argt.append(c_void_p)
+            else:
+                argt.append(_CT[a.replace("const ", "").split()[0]])
+        sigs[name] = ({"int": c_int, "int64_t": c_int64, "const char*": c_char_p, "void": None}[ret], argt)
+    return sigs
+
+
+_SIGS = _parse_header()
 
 _lib = None
 

@@ -1,0 +1,588 @@
+// Training-path kernels (forward with saved statistics + backward), fp32 SIMT.  First complete version of the
+// backward pass of the CMDM denoiser: correctness first — unfused, grouped tensors of the
+// point-cloud encoder are materialised here (unlike the fused eval kernels), tensor-core versions are the next step.
+// Reference semantics: torch autograd through models/cmdm.py:118-196, models/scene_models/pointtransformer.py:9-123
+// (train-mode BatchNorm1d = batch statistics), diffusion/gaussian_diffusion.py:815-822 (masked MSE).
+#include <math_constants.h>
+#include "common.cuh"
+
+namespace {
+
+constexpr int TB = 256;
+inline int grid_for(int64_t n, int per_block = TB) {
+    int64_t b = (n + per_block - 1) / per_block;
+    int64_t cap = (int64_t)AM_NUM_SMS * 16;
+    return (int)(b < 1 ? 1 : (b < cap ? b : cap));
+}
+#define GRID_STRIDE(i, n) for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (n); i += (int64_t)gridDim.x * blockDim.x)
+
+// ---------------------------------------------------------------- general batched GEMM (row-major, optional transposes)
+struct GemmG {
+    const float* A; const float* B; float* C;
+    int M, N, K, lda, ldb, ldc, transA, transB;
+    float alpha, beta;
+    int bdiv; int64_t sA1, sA2, sB1, sB2, sC1, sC2;
+};
+
+__global__ void __launch_bounds__(256) gemm_general_kernel(GemmG g) {
+    constexpr int BT = 64, BK = 16;
+    __shared__ float As[BK][BT + 1];
+    __shared__ float Bs[BK][BT + 1];
+    const int bi = blockIdx.z;
+    const float* A = g.A + (bi / g.bdiv) * g.sA1 + (bi % g.bdiv) * g.sA2;
+    const float* B = g.B + (bi / g.bdiv) * g.sB1 + (bi % g.bdiv) * g.sB2;
+    float* C = g.C + (bi / g.bdiv) * g.sC1 + (bi % g.bdiv) * g.sC2;
+    const int m0 = blockIdx.y * BT, n0 = blockIdx.x * BT;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < g.K; k0 += BK) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int idx = tid + i * 256;
+            int m, k;
+            if (g.transA) { m = idx & 63; k = idx >> 6; } else { k = idx & 15; m = idx >> 4; }
+            int gm = m0 + m, gk = k0 + k;
+            float v = 0.f;
+            if (gm < g.M && gk < g.K) v = g.transA ? A[(int64_t)gk * g.lda + gm] : A[(int64_t)gm * g.lda + gk];
+            As[k][m] = v;
+            int n;
+            if (g.transB) { k = idx & 15; n = idx >> 4; } else { n = idx & 63; k = idx >> 6; }
+            int gn = n0 + n; gk = k0 + k;
+            v = 0.f;
+            if (gn < g.N && gk < g.K) v = g.transB ? B[(int64_t)gn * g.ldb + gk] : B[(int64_t)gk * g.ldb + gn];
+            Bs[k][n] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = As[k][ty * 4 + i]; b[i] = Bs[k][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int m = m0 + ty * 4 + i;
+        if (m >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int n = n0 + tx * 4 + j;
+            if (n >= g.N) continue;
+            float* c = C + (int64_t)m * g.ldc + n;
+            float v = g.alpha * acc[i][j];
+            if (g.beta != 0.f) v += g.beta * *c;
+            *c = v;
+        }
+    }
+}
+
+// out[n] = beta*out[n] + sum_m X[m][n]
+__global__ void colsum_kernel(const float* __restrict__ X, int ldx, float* __restrict__ out, int M, int N, float beta) {
+    __shared__ float red[8][33];
+    int n = blockIdx.x * 32 + (threadIdx.x & 31);
+    int r = threadIdx.x >> 5;
+    float s = 0.f;
+    if (n < N)
+        for (int m = r; m < M; m += 8) s += X[(int64_t)m * ldx + n];
+    red[r][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (r == 0 && n < N) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x & 31];
+        out[n] = (beta != 0.f ? beta * out[n] : 0.f) + t;
+    }
+}
+
+// ---------------------------------------------------------------- elementwise
+__global__ void gelu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) { GRID_STRIDE(i, n) y[i] = gelu_erf(x[i]); }
+__global__ void gelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dx, int64_t n) {
+    GRID_STRIDE(i, n) {
+        float v = x[i];
+        float cdf = 0.5f * (1.0f + erff(v * 0.70710678118654752440f));
+        float pdf = 0.39894228040143267794f * expf(-0.5f * v * v);
+        dx[i] = dy[i] * (cdf + v * pdf);
+    }
+}
+__global__ void relu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dx, int64_t n) {
+    GRID_STRIDE(i, n) dx[i] = y[i] > 0.f ? dy[i] : 0.f;
+}
+__global__ void add_relu_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, int64_t n, int relu) {
+    GRID_STRIDE(i, n) { float v = a[i] + b[i]; y[i] = relu ? fmaxf(v, 0.f) : v; }
+}
+// inverted dropout with a counter-based mask: the same call on gradients is the backward
+__global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, float p, uint64_t seed, uint32_t site) {
+    const float scale = 1.0f / (1.0f - p);
+    int64_t nblk = (n + 3) / 4;
+    GRID_STRIDE(bk, nblk) {
+        Philox4 r = philox4x32_10((uint32_t)bk, (uint32_t)(bk >> 32), site, 0x44524F50u, (uint32_t)seed, (uint32_t)(seed >> 32));
+        uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int64_t i = bk * 4 + j;
+            if (i < n) y[i] = (u01(w[j]) >= p) ? x[i] * scale : 0.f;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- LayerNorm backward (one warp per row, D <= 1024)
+template <int MAXV>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ X, const float* __restrict__ R,
+                                                            const float* __restrict__ gamma, float* __restrict__ dX, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, int M, int D, float eps) {
+    extern __shared__ float sacc[];  // [2][D] per-CTA partial dgamma / dbeta
+    for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sacc[i] = 0.f;
+    __syncthreads();
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (row < M) {
+        const float* x = X + (int64_t)row * D;
+        const float* r = R ? R + (int64_t)row * D : nullptr;
+        const float* dy = dY + (int64_t)row * D;
+        float v[MAXV], g[MAXV];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            int d = lane + i * 32;
+            float t = 0.f;
+            if (d < D) { t = x[d]; if (r) t += r[d]; }
+            v[i] = t; s += t;
+        }
+        float mean = warp_sum(s) / (float)D;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) { int d = lane + i * 32; float t = d < D ? v[i] - mean : 0.f; q += t * t; }
+        float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            int d = lane + i * 32;
+            float xh = d < D ? (v[i] - mean) * rstd : 0.f;
+            float dyv = d < D ? dy[d] : 0.f;
+            float dxh = d < D ? dyv * gamma[d] : 0.f;
+            v[i] = xh; g[i] = dxh;
+            s1 += dxh; s2 += dxh * xh;
+            if (d < D) { atomicAdd(&sacc[d], dyv * xh); atomicAdd(&sacc[D + d], dyv); }
+        }
+        s1 = warp_sum(s1) / (float)D; s2 = warp_sum(s2) / (float)D;
+        float* dx = dX + (int64_t)row * D;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) { int d = lane + i * 32; if (d < D) dx[d] = rstd * (g[i] - s1 - v[i] * s2); }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < D; i += blockDim.x) { atomicAdd(&dgamma[i], sacc[i]); atomicAdd(&dbeta[i], sacc[D + i]); }
+}
+
+// ---------------------------------------------------------------- attention pieces (scores / probs are [B*H, Sq, Sk] buffers)
+// in place: P = softmax(scale * S + key mask) over the last dim; one warp per row
+__global__ void softmax_rows_fwd_kernel(float* __restrict__ S, const uint8_t* __restrict__ key_pad, int rows, int Sk, int rows_per_batch, float scale) {
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    int lane = threadIdx.x & 31;
+    float* s = S + (int64_t)row * Sk;
+    const uint8_t* pad = key_pad ? key_pad + (int64_t)(row / rows_per_batch) * Sk : nullptr;
+    float mx = -CUDART_INF_F;
+    for (int k = lane; k < Sk; k += 32) if (!(pad && pad[k])) mx = fmaxf(mx, s[k] * scale);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int k = lane; k < Sk; k += 32) {
+        float e = (pad && pad[k]) ? 0.f : expf(s[k] * scale - mx);
+        s[k] = e; sum += e;
+    }
+    sum = warp_sum(sum);
+    float inv = 1.f / sum;
+    for (int k = lane; k < Sk; k += 32) s[k] *= inv;
+}
+// in place on dP: dS = scale * P * (dP - sum_k dP*P)
+__global__ void softmax_rows_bwd_kernel(float* __restrict__ dP, const float* __restrict__ P, int rows, int Sk, float scale) {
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    int lane = threadIdx.x & 31;
+    float* d = dP + (int64_t)row * Sk;
+    const float* p = P + (int64_t)row * Sk;
+    float s = 0.f;
+    for (int k = lane; k < Sk; k += 32) s += d[k] * p[k];
+    s = warp_sum(s);
+    for (int k = lane; k < Sk; k += 32) d[k] = scale * p[k] * (d[k] - s);
+}
+
+// ---------------------------------------------------------------- BatchNorm1d (train): column statistics over M rows
+__global__ void bn_stats_kernel(const float* __restrict__ X, int M, int C, double* __restrict__ acc /*[2C] sum, sumsq*/) {
+    // thread -> column (c = tid % Cp), rows strided; coalesced along C
+    extern __shared__ float sh[];  // [2][blockDim.x]
+    int Cp = C;  // columns handled per pass = min(C, blockDim.x)
+    int cols = Cp < (int)blockDim.x ? Cp : (int)blockDim.x;
+    int rpb = blockDim.x / cols;  // rows in flight per block
+    int c = threadIdx.x % cols, rr = threadIdx.x / cols;
+    for (int c0 = 0; c0 < C; c0 += cols) {
+        int col = c0 + c;
+        float s = 0.f, q = 0.f;
+        if (rr < rpb && col < C)
+            for (int64_t m = (int64_t)blockIdx.x * rpb + rr; m < M; m += (int64_t)gridDim.x * rpb) { float v = X[m * C + col]; s += v; q += v * v; }
+        sh[threadIdx.x] = s; sh[blockDim.x + threadIdx.x] = q;
+        __syncthreads();
+        if (rr == 0 && col < C) {
+            float ts = 0.f, tq = 0.f;
+            for (int i = 0; i < rpb; ++i) { ts += sh[i * cols + c]; tq += sh[blockDim.x + i * cols + c]; }
+            atomicAdd(&acc[col], (double)ts); atomicAdd(&acc[C + col], (double)tq);
+        }
+        __syncthreads();
+    }
+}
+__global__ void bn_finalize_kernel(const double* __restrict__ acc, int M, int C, float eps, float* __restrict__ mean, float* __restrict__ invstd,
+                                   float* __restrict__ var_biased) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double mu = acc[c] / M;
+    double var = acc[C + c] / M - mu * mu;
+    if (var < 0) var = 0;
+    mean[c] = (float)mu; var_biased[c] = (float)var; invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+}
+__global__ void bn_apply_kernel(const float* __restrict__ X, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ Y, int64_t total, int C, int relu) {
+    GRID_STRIDE(i, total) {
+        int c = (int)(i % C);
+        float v = (X[i] - mean[c]) * invstd[c] * gamma[c] + beta[c];
+        Y[i] = relu ? fmaxf(v, 0.f) : v;
+    }
+}
+// pass 1 of backward: acc[c] += sum dy', acc[C+c] += sum dy' * xhat   (dy' = dy masked by relu)
+__global__ void bn_bwd_reduce_kernel(const float* __restrict__ dY, const float* __restrict__ X, const float* __restrict__ Y, const float* __restrict__ mean,
+                                     const float* __restrict__ invstd, int M, int C, int relu, double* __restrict__ acc) {
+    extern __shared__ float sh[];
+    int cols = C < (int)blockDim.x ? C : (int)blockDim.x;
+    int rpb = blockDim.x / cols;
+    int c = threadIdx.x % cols, rr = threadIdx.x / cols;
+    for (int c0 = 0; c0 < C; c0 += cols) {
+        int col = c0 + c;
+        float s = 0.f, q = 0.f;
+        if (rr < rpb && col < C) {
+            float mu = mean[col], is = invstd[col];
+            for (int64_t m = (int64_t)blockIdx.x * rpb + rr; m < M; m += (int64_t)gridDim.x * rpb) {
+                float dy = dY[m * C + col];
+                if (relu && !(Y[m * C + col] > 0.f)) dy = 0.f;
+                s += dy; q += dy * (X[m * C + col] - mu) * is;
+            }
+        }
+        sh[threadIdx.x] = s; sh[blockDim.x + threadIdx.x] = q;
+        __syncthreads();
+        if (rr == 0 && col < C) {
+            float ts = 0.f, tq = 0.f;
+            for (int i = 0; i < rpb; ++i) { ts += sh[i * cols + c]; tq += sh[blockDim.x + i * cols + c]; }
+            atomicAdd(&acc[col], (double)ts); atomicAdd(&acc[C + col], (double)tq);
+        }
+        __syncthreads();
+    }
+}
+// pass 2: dX = gamma*invstd * (dy' - dbeta/M - xhat*dgamma/M); also writes dgamma / dbeta (float) once
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ dY, const float* __restrict__ X, const float* __restrict__ Y, const float* __restrict__ mean,
+                                    const float* __restrict__ invstd, const float* __restrict__ gamma, const double* __restrict__ acc, float* __restrict__ dX,
+                                    int64_t total, int M, int C, int relu) {
+    GRID_STRIDE(i, total) {
+        int c = (int)(i % C);
+        float dy = dY[i];
+        if (relu && !(Y[i] > 0.f)) dy = 0.f;
+        float xh = (X[i] - mean[c]) * invstd[c];
+        float db = (float)(acc[c] / M), dg = (float)(acc[C + c] / M);
+        dX[i] = gamma[c] * invstd[c] * (dy - db - xh * dg);
+    }
+}
+__global__ void acc_to_float_kernel(const double* __restrict__ acc, float* __restrict__ dgamma, float* __restrict__ dbeta, int C) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C) { dbeta[c] += (float)acc[c]; dgamma[c] += (float)acc[C + c]; }
+}
+
+// ---------------------------------------------------------------- gather / scatter and grouped point ops
+__global__ void scatter_add_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, float* __restrict__ dst, int64_t m, int c,
+                                        int src_ld, int src_off) {
+    GRID_STRIDE(g, m * c) {
+        int64_t i = g / c; int j = (int)(g - i * c);
+        atomicAdd(&dst[(int64_t)idx[i] * c + j], src[i * src_ld + src_off + j]);
+    }
+}
+// rel[i*k+j, :] = p[idx[i,j]] - q[i]   (q = query points; grouped relative coordinates, pointops.py:91-93)
+__global__ void group_rel_kernel(const float* __restrict__ p, const float* __restrict__ q, const int32_t* __restrict__ idx, float* __restrict__ rel,
+                                 int64_t m, int k) {
+    GRID_STRIDE(g, m * k) {
+        int64_t i = g / k;
+        int nb = idx[g];
+        rel[g * 3 + 0] = p[3 * (int64_t)nb] - q[3 * i]; rel[g * 3 + 1] = p[3 * (int64_t)nb + 1] - q[3 * i + 1]; rel[g * 3 + 2] = p[3 * (int64_t)nb + 2] - q[3 * i + 2];
+    }
+}
+// G[i*k+j, :] = cat(rel[i*k+j, 0:3], x[idx[i,j], :])    (TransitionDown grouped input, pointtransformer.py:63)
+__global__ void group_cat_kernel(const float* __restrict__ rel, const float* __restrict__ x, const int32_t* __restrict__ idx, float* __restrict__ G,
+                                 int64_t mk, int c) {
+    int w = 3 + c;
+    GRID_STRIDE(g, mk * w) {
+        int64_t r = g / w; int j = (int)(g - r * w);
+        G[g] = j < 3 ? rel[r * 3 + j] : x[(int64_t)idx[r] * c + (j - 3)];
+    }
+}
+// w[i,j,:] = kf[idx[i,j],:] - qf[i,:] + pr[i,j,:]   (qkv packed [n,3c]: q | k | v)
+__global__ void pt_w_fwd_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ idx, const float* __restrict__ pr, float* __restrict__ w,
+                                int64_t n, int k, int c) {
+    GRID_STRIDE(g, n * k * c) {
+        int ch = (int)(g % c); int64_t r = g / c; int64_t i = r / k;
+        w[g] = qkv[(int64_t)idx[r] * 3 * c + c + ch] - qkv[i * 3 * c + ch] + pr[g];
+    }
+}
+// backward of pt_w: dqkv[idx].k += dw ; dqkv[i].q -= dw ; dpr += dw
+__global__ void pt_w_bwd_kernel(const float* __restrict__ dw, const int32_t* __restrict__ idx, float* __restrict__ dqkv, float* __restrict__ dpr,
+                                int64_t n, int k, int c) {
+    GRID_STRIDE(g, n * k * c) {
+        int ch = (int)(g % c); int64_t r = g / c; int64_t i = r / k;
+        float d = dw[g];
+        atomicAdd(&dqkv[(int64_t)idx[r] * 3 * c + c + ch], d);
+        atomicAdd(&dqkv[i * 3 * c + ch], -d);
+        dpr[g] += d;
+    }
+}
+// softmax over the k neighbours (dim 1 of [n,k,c8]); in place
+__global__ void softmax_k_fwd_kernel(float* __restrict__ w, int64_t n, int k, int c8) {
+    GRID_STRIDE(g, n * c8) {
+        int64_t i = g / c8; int o = (int)(g - i * c8);
+        float* base = w + i * k * c8 + o;
+        float mx = -CUDART_INF_F;
+        for (int j = 0; j < k; ++j) mx = fmaxf(mx, base[(int64_t)j * c8]);
+        float s = 0.f;
+        for (int j = 0; j < k; ++j) { float e = expf(base[(int64_t)j * c8] - mx); base[(int64_t)j * c8] = e; s += e; }
+        float inv = 1.f / s;
+        for (int j = 0; j < k; ++j) base[(int64_t)j * c8] *= inv;
+    }
+}
+__global__ void softmax_k_bwd_kernel(float* __restrict__ dw, const float* __restrict__ w, int64_t n, int k, int c8) {
+    GRID_STRIDE(g, n * c8) {
+        int64_t i = g / c8; int o = (int)(g - i * c8);
+        float* d = dw + i * k * c8 + o;
+        const float* p = w + i * k * c8 + o;
+        float s = 0.f;
+        for (int j = 0; j < k; ++j) s += d[(int64_t)j * c8] * p[(int64_t)j * c8];
+        for (int j = 0; j < k; ++j) d[(int64_t)j * c8] = p[(int64_t)j * c8] * (d[(int64_t)j * c8] - s);
+    }
+}
+// out[i, ch] = sum_j (v[idx[i,j], ch] + pr[i,j,ch]) * ws[i,j, ch % c8]
+__global__ void pt_agg_fwd_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ idx, const float* __restrict__ pr, const float* __restrict__ ws,
+                                  float* __restrict__ out, int64_t n, int k, int c) {
+    int c8 = c / 8;
+    GRID_STRIDE(g, n * c) {
+        int64_t i = g / c; int ch = (int)(g - i * c);
+        float acc = 0.f;
+        for (int j = 0; j < k; ++j) {
+            int64_t r = i * k + j;
+            acc = fmaf(qkv[(int64_t)idx[r] * 3 * c + 2 * c + ch] + pr[r * c + ch], ws[r * c8 + (ch % c8)], acc);
+        }
+        out[g] = acc;
+    }
+}
+// backward of pt_agg: dv[idx] += ws*dout ; dpr = ws*dout (overwrite) ; dws[i,j,o] = sum_g (v+pr)[g*c8+o]*dout[g*c8+o]
+__global__ void pt_agg_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ qkv, const int32_t* __restrict__ idx, const float* __restrict__ pr,
+                                  const float* __restrict__ ws, float* __restrict__ dqkv, float* __restrict__ dpr, float* __restrict__ dws, int64_t n, int k, int c) {
+    int c8 = c / 8;
+    GRID_STRIDE(g, n * k * c8) {
+        int o = (int)(g % c8); int64_t r = g / c8; int64_t i = r / k;
+        int nb = idx[r];
+        float wv = ws[g];
+        float dacc = 0.f;
+        for (int gq = 0; gq < 8; ++gq) {
+            int ch = gq * c8 + o;
+            float d = dout[i * c + ch];
+            dacc = fmaf(qkv[(int64_t)nb * 3 * c + 2 * c + ch] + pr[r * c + ch], d, dacc);
+            atomicAdd(&dqkv[(int64_t)nb * 3 * c + 2 * c + ch], wv * d);
+            dpr[r * c + ch] = wv * d;
+        }
+        dws[g] = dacc;
+    }
+}
+// max over the k grouped rows with argmax (MaxPool1d(nsample), pointtransformer.py:65)
+__global__ void maxpool_k_fwd_kernel(const float* __restrict__ Z, float* __restrict__ out, int32_t* __restrict__ arg, int64_t m, int k, int c) {
+    GRID_STRIDE(g, m * c) {
+        int64_t i = g / c; int ch = (int)(g - i * c);
+        float best = -CUDART_INF_F; int bj = 0;
+        for (int j = 0; j < k; ++j) { float v = Z[(i * k + j) * c + ch]; if (v > best) { best = v; bj = j; } }
+        out[g] = best; arg[g] = bj;
+    }
+}
+__global__ void maxpool_k_bwd_kernel(const float* __restrict__ dout, const int32_t* __restrict__ arg, float* __restrict__ dZ, int64_t m, int k, int c) {
+    GRID_STRIDE(g, m * k * c) {
+        int ch = (int)(g % c); int64_t r = g / c; int64_t i = r / k; int j = (int)(r - i * k);
+        dZ[g] = arg[i * c + ch] == j ? dout[i * c + ch] : 0.f;
+    }
+}
+// d(loss.mean())/d pred for the masked MSE: 2 (pred - x0) * !mask / (cnt_b * D) * gscale[b]
+__global__ void masked_mse_bwd_kernel(const float* __restrict__ x0, const float* __restrict__ pred, const uint8_t* __restrict__ mask,
+                                      const float* __restrict__ gloss, float* __restrict__ dpred, int B, int T, int D) {
+    int b = blockIdx.x;
+    __shared__ float s_cnt;
+    if (threadIdx.x == 0) { float c = 0.f; for (int l = 0; l < T; ++l) c += (mask && mask[(int64_t)b * T + l]) ? 0.f : 1.f; s_cnt = c; }
+    __syncthreads();
+    float sc = 2.0f * gloss[b] / (s_cnt * (float)D);
+    for (int i = threadIdx.x; i < T * D; i += blockDim.x) {
+        int l = i / D;
+        bool keep = !(mask && mask[(int64_t)b * T + l]);
+        int64_t g = (int64_t)b * T * D + i;
+        dpred[g] = keep ? sc * (pred[g] - x0[g]) : 0.f;
+    }
+}
+
+}  // namespace
+
+#define ST as_stream(stream)
+
+extern "C" int am_gemm_f32(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb, float beta,
+                           float* C, int ldc, int batch, int bdiv, int64_t sA1, int64_t sA2, int64_t sB1, int64_t sB2, int64_t sC1, int64_t sC2,
+                           am_stream_t stream) {
+    AM_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && batch > 0 && bdiv > 0, AM_EINVAL, "am_gemm_f32: bad args");
+    GemmG g{A, B, C, M, N, K, lda, ldb, ldc, transA, transB, alpha, beta, bdiv, sA1, sA2, sB1, sB2, sC1, sC2};
+    dim3 grid(cdiv(N, 64), cdiv(M, 64), batch);
+    gemm_general_kernel<<<grid, 256, 0, ST>>>(g);
+    AM_LAUNCH_CHECK("gemm_f32");
+    return AM_OK;
+}
+extern "C" int am_colsum_f32(const float* X, int ldx, float* out, int M, int N, float beta, am_stream_t stream) {
+    AM_REQUIRE(X && out && M > 0 && N > 0, AM_EINVAL, "am_colsum_f32: bad args");
+    colsum_kernel<<<cdiv(N, 32), 256, 0, ST>>>(X, ldx, out, M, N, beta);
+    AM_LAUNCH_CHECK("colsum");
+    return AM_OK;
+}
+extern "C" int am_gelu_fwd(const float* x, float* y, int64_t n, am_stream_t stream) {
+    AM_REQUIRE(x && y && n > 0, AM_EINVAL, "am_gelu_fwd: bad args");
+    gelu_fwd_kernel<<<grid_for(n), TB, 0, ST>>>(x, y, n); AM_LAUNCH_CHECK("gelu_fwd"); return AM_OK;
+}
+extern "C" int am_gelu_bwd(const float* dy, const float* x, float* dx, int64_t n, am_stream_t stream) {
+    AM_REQUIRE(dy && x && dx && n > 0, AM_EINVAL, "am_gelu_bwd: bad args");
+    gelu_bwd_kernel<<<grid_for(n), TB, 0, ST>>>(dy, x, dx, n); AM_LAUNCH_CHECK("gelu_bwd"); return AM_OK;
+}
+extern "C" int am_relu_bwd(const float* dy, const float* y, float* dx, int64_t n, am_stream_t stream) {
+    AM_REQUIRE(dy && y && dx && n > 0, AM_EINVAL, "am_relu_bwd: bad args");
+    relu_bwd_kernel<<<grid_for(n), TB, 0, ST>>>(dy, y, dx, n); AM_LAUNCH_CHECK("relu_bwd"); return AM_OK;
+}
+extern "C" int am_add_f32(const float* a, const float* b, float* y, int64_t n, int relu, am_stream_t stream) {
+    AM_REQUIRE(a && b && y && n > 0, AM_EINVAL, "am_add_f32: bad args");
+    add_relu_kernel<<<grid_for(n), TB, 0, ST>>>(a, b, y, n, relu); AM_LAUNCH_CHECK("add_f32"); return AM_OK;
+}
+extern "C" int am_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, uint32_t site, am_stream_t stream) {
+    AM_REQUIRE(x && y && n > 0 && p >= 0.f && p < 1.f, AM_EINVAL, "am_dropout: bad args");
+    dropout_kernel<<<grid_for((n + 3) / 4), TB, 0, ST>>>(x, y, n, p, seed, site); AM_LAUNCH_CHECK("dropout"); return AM_OK;
+}
+extern "C" int am_layernorm_bwd(const float* dY, const float* X, const float* R, const float* gamma, float* dX, float* dgamma, float* dbeta, int M,
+                                int D, float eps, am_stream_t stream) {
+    AM_REQUIRE(dY && X && gamma && dX && dgamma && dbeta && M > 0 && D > 0 && D <= 1024, AM_EINVAL, "am_layernorm_bwd: bad args");
+    size_t sm = sizeof(float) * 2 * D;
+    int grid = cdiv(M, 8);
+    if (D <= 256) layernorm_bwd_kernel<8><<<grid, 256, sm, ST>>>(dY, X, R, gamma, dX, dgamma, dbeta, M, D, eps);
+    else if (D <= 512) layernorm_bwd_kernel<16><<<grid, 256, sm, ST>>>(dY, X, R, gamma, dX, dgamma, dbeta, M, D, eps);
+    else layernorm_bwd_kernel<32><<<grid, 256, sm, ST>>>(dY, X, R, gamma, dX, dgamma, dbeta, M, D, eps);
+    AM_LAUNCH_CHECK("layernorm_bwd");
+    return AM_OK;
+}
+extern "C" int am_softmax_rows_fwd(float* S, const uint8_t* key_pad, int rows, int Sk, int rows_per_batch, float scale, am_stream_t stream) {
+    AM_REQUIRE(S && rows > 0 && Sk > 0 && rows_per_batch > 0, AM_EINVAL, "am_softmax_rows_fwd: bad args");
+    softmax_rows_fwd_kernel<<<cdiv(rows, 8), 256, 0, ST>>>(S, key_pad, rows, Sk, rows_per_batch, scale); AM_LAUNCH_CHECK("softmax_rows_fwd"); return AM_OK;
+}
+extern "C" int am_softmax_rows_bwd(float* dP, const float* P, int rows, int Sk, float scale, am_stream_t stream) {
+    AM_REQUIRE(dP && P && rows > 0 && Sk > 0, AM_EINVAL, "am_softmax_rows_bwd: bad args");
+    softmax_rows_bwd_kernel<<<cdiv(rows, 8), 256, 0, ST>>>(dP, P, rows, Sk, scale); AM_LAUNCH_CHECK("softmax_rows_bwd"); return AM_OK;
+}
+// acc: [2C] doubles zeroed by the caller.  Writes batch mean / invstd / biased variance.
+extern "C" int am_bn_train_stats(const float* X, int M, int C, float eps, double* acc, float* mean, float* invstd, float* var_biased, am_stream_t stream) {
+    AM_REQUIRE(X && acc && mean && invstd && var_biased && M > 0 && C > 0, AM_EINVAL, "am_bn_train_stats: bad args");
+    int rows_per_blk = 256 / (C < 256 ? C : 256); if (rows_per_blk < 1) rows_per_blk = 1;
+    int grid = (int)(cdiv(M, rows_per_blk * 64) < AM_NUM_SMS * 8 ? cdiv(M, rows_per_blk * 64) : AM_NUM_SMS * 8);
+    bn_stats_kernel<<<grid, 256, sizeof(float) * 512, ST>>>(X, M, C, acc);
+    AM_LAUNCH_CHECK("bn_stats");
+    bn_finalize_kernel<<<cdiv(C, 128), 128, 0, ST>>>(acc, M, C, eps, mean, invstd, var_biased);
+    AM_LAUNCH_CHECK("bn_finalize");
+    return AM_OK;
+}
+extern "C" int am_bn_apply(const float* X, const float* mean, const float* invstd, const float* gamma, const float* beta, float* Y, int M, int C, int relu,
+                           am_stream_t stream) {
+    AM_REQUIRE(X && mean && invstd && gamma && beta && Y && M > 0 && C > 0, AM_EINVAL, "am_bn_apply: bad args");
+    bn_apply_kernel<<<grid_for((int64_t)M * C), TB, 0, ST>>>(X, mean, invstd, gamma, beta, Y, (int64_t)M * C, C, relu); AM_LAUNCH_CHECK("bn_apply"); return AM_OK;
+}
+// acc: [2C] doubles zeroed by the caller; dgamma / dbeta are ACCUMULATED into.
+extern "C" int am_bn_bwd(const float* dY, const float* X, const float* Y, const float* mean, const float* invstd, const float* gamma, double* acc, float* dX,
+                         float* dgamma, float* dbeta, int M, int C, int relu, am_stream_t stream) {
+    AM_REQUIRE(dY && X && mean && invstd && gamma && acc && dX && dgamma && dbeta && M > 0 && C > 0 && (!relu || Y), AM_EINVAL, "am_bn_bwd: bad args");
+    int rows_per_blk = 256 / (C < 256 ? C : 256); if (rows_per_blk < 1) rows_per_blk = 1;
+    int grid = (int)(cdiv(M, rows_per_blk * 64) < AM_NUM_SMS * 8 ? cdiv(M, rows_per_blk * 64) : AM_NUM_SMS * 8);
+    bn_bwd_reduce_kernel<<<grid, 256, sizeof(float) * 512, ST>>>(dY, X, Y, mean, invstd, M, C, relu, acc);
+    AM_LAUNCH_CHECK("bn_bwd_reduce");
+    bn_bwd_apply_kernel<<<grid_for((int64_t)M * C), TB, 0, ST>>>(dY, X, Y, mean, invstd, gamma, acc, dX, (int64_t)M * C, M, C, relu);
+    AM_LAUNCH_CHECK("bn_bwd_apply");
+    acc_to_float_kernel<<<cdiv(C, 128), 128, 0, ST>>>(acc, dgamma, dbeta, C);
+    AM_LAUNCH_CHECK("bn_bwd_acc");
+    return AM_OK;
+}
+extern "C" int am_scatter_add_rows(const float* src, int src_ld, int src_off, const int32_t* idx, float* dst, int64_t m, int c, am_stream_t stream) {
+    AM_REQUIRE(src && idx && dst && m > 0 && c > 0, AM_EINVAL, "am_scatter_add_rows: bad args");
+    scatter_add_rows_kernel<<<grid_for(m * c), TB, 0, ST>>>(src, idx, dst, m, c, src_ld, src_off); AM_LAUNCH_CHECK("scatter_add_rows"); return AM_OK;
+}
+extern "C" int am_group_rel(const float* p, const float* q, const int32_t* idx, float* rel, int64_t m, int k, am_stream_t stream) {
+    AM_REQUIRE(p && q && idx && rel && m > 0 && k > 0, AM_EINVAL, "am_group_rel: bad args");
+    group_rel_kernel<<<grid_for(m * k), TB, 0, ST>>>(p, q, idx, rel, m, k); AM_LAUNCH_CHECK("group_rel"); return AM_OK;
+}
+extern "C" int am_group_cat(const float* rel, const float* x, const int32_t* idx, float* G, int64_t mk, int c, am_stream_t stream) {
+    AM_REQUIRE(rel && x && idx && G && mk > 0 && c > 0, AM_EINVAL, "am_group_cat: bad args");
+    group_cat_kernel<<<grid_for(mk * (3 + c)), TB, 0, ST>>>(rel, x, idx, G, mk, c); AM_LAUNCH_CHECK("group_cat"); return AM_OK;
+}
+extern "C" int am_pt_w_fwd(const float* qkv, const int32_t* idx, const float* pr, float* w, int64_t n, int k, int c, am_stream_t stream) {
+    AM_REQUIRE(qkv && idx && pr && w && n > 0, AM_EINVAL, "am_pt_w_fwd: bad args");
+    pt_w_fwd_kernel<<<grid_for(n * k * c), TB, 0, ST>>>(qkv, idx, pr, w, n, k, c); AM_LAUNCH_CHECK("pt_w_fwd"); return AM_OK;
+}
+extern "C" int am_pt_w_bwd(const float* dw, const int32_t* idx, float* dqkv, float* dpr, int64_t n, int k, int c, am_stream_t stream) {
+    AM_REQUIRE(dw && idx && dqkv && dpr && n > 0, AM_EINVAL, "am_pt_w_bwd: bad args");
+    pt_w_bwd_kernel<<<grid_for(n * k * c), TB, 0, ST>>>(dw, idx, dqkv, dpr, n, k, c); AM_LAUNCH_CHECK("pt_w_bwd"); return AM_OK;
+}
+extern "C" int am_softmax_k_fwd(float* w, int64_t n, int k, int c8, am_stream_t stream) {
+    AM_REQUIRE(w && n > 0 && k > 0 && c8 > 0, AM_EINVAL, "am_softmax_k_fwd: bad args");
+    softmax_k_fwd_kernel<<<grid_for(n * c8), TB, 0, ST>>>(w, n, k, c8); AM_LAUNCH_CHECK("softmax_k_fwd"); return AM_OK;
+}
+extern "C" int am_softmax_k_bwd(float* dw, const float* w, int64_t n, int k, int c8, am_stream_t stream) {
+    AM_REQUIRE(dw && w && n > 0, AM_EINVAL, "am_softmax_k_bwd: bad args");
+    softmax_k_bwd_kernel<<<grid_for(n * c8), TB, 0, ST>>>(dw, w, n, k, c8); AM_LAUNCH_CHECK("softmax_k_bwd"); return AM_OK;
+}
+extern "C" int am_pt_agg_fwd(const float* qkv, const int32_t* idx, const float* pr, const float* ws, float* out, int64_t n, int k, int c, am_stream_t stream) {
+    AM_REQUIRE(qkv && idx && pr && ws && out && n > 0 && c % 8 == 0, AM_EINVAL, "am_pt_agg_fwd: bad args");
+    pt_agg_fwd_kernel<<<grid_for(n * c), TB, 0, ST>>>(qkv, idx, pr, ws, out, n, k, c); AM_LAUNCH_CHECK("pt_agg_fwd"); return AM_OK;
+}
+extern "C" int am_pt_agg_bwd(const float* dout, const float* qkv, const int32_t* idx, const float* pr, const float* ws, float* dqkv, float* dpr, float* dws,
+                             int64_t n, int k, int c, am_stream_t stream) {
+    AM_REQUIRE(dout && qkv && idx && pr && ws && dqkv && dpr && dws && n > 0 && c % 8 == 0, AM_EINVAL, "am_pt_agg_bwd: bad args");
+    pt_agg_bwd_kernel<<<grid_for(n * k * (c / 8)), TB, 0, ST>>>(dout, qkv, idx, pr, ws, dqkv, dpr, dws, n, k, c); AM_LAUNCH_CHECK("pt_agg_bwd"); return AM_OK;
+}
+extern "C" int am_maxpool_k_fwd(const float* Z, float* out, int32_t* arg, int64_t m, int k, int c, am_stream_t stream) {
+    AM_REQUIRE(Z && out && arg && m > 0, AM_EINVAL, "am_maxpool_k_fwd: bad args");
+    maxpool_k_fwd_kernel<<<grid_for(m * c), TB, 0, ST>>>(Z, out, arg, m, k, c); AM_LAUNCH_CHECK("maxpool_k_fwd"); return AM_OK;
+}
+extern "C" int am_maxpool_k_bwd(const float* dout, const int32_t* arg, float* dZ, int64_t m, int k, int c, am_stream_t stream) {
+    AM_REQUIRE(dout && arg && dZ && m > 0, AM_EINVAL, "am_maxpool_k_bwd: bad args");
+    maxpool_k_bwd_kernel<<<grid_for(m * k * c), TB, 0, ST>>>(dout, arg, dZ, m, k, c); AM_LAUNCH_CHECK("maxpool_k_bwd"); return AM_OK;
+}
+extern "C" int am_masked_mse_bwd(const float* x0, const float* pred, const uint8_t* mask, const float* gloss, float* dpred, int B, int T, int D,
+                                 am_stream_t stream) {
+    AM_REQUIRE(x0 && pred && gloss && dpred && B > 0 && T > 0 && D > 0, AM_EINVAL, "am_masked_mse_bwd: bad args");
+    masked_mse_bwd_kernel<<<B, 512, 0, ST>>>(x0, pred, mask, gloss, dpred, B, T, D); AM_LAUNCH_CHECK("masked_mse_bwd"); return AM_OK;
+}
+
+namespace {
+__global__ void silu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) { GRID_STRIDE(i, n) y[i] = silu_f(x[i]); }
+__global__ void silu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dx, int64_t n) {
+    GRID_STRIDE(i, n) { float v = x[i]; float s = 1.0f / (1.0f + expf(-v)); dx[i] = dy[i] * s * (1.0f + v * (1.0f - s)); }
+}
+}  // namespace
+extern "C" int am_silu_fwd(const float* x, float* y, int64_t n, am_stream_t stream) {
+    AM_REQUIRE(x && y && n > 0, AM_EINVAL, "am_silu_fwd: bad args");
+    silu_fwd_kernel<<<grid_for(n), TB, 0, ST>>>(x, y, n); AM_LAUNCH_CHECK("silu_fwd"); return AM_OK;
+}
+extern "C" int am_silu_bwd(const float* dy, const float* x, float* dx, int64_t n, am_stream_t stream) {
+    AM_REQUIRE(dy && x && dx && n > 0, AM_EINVAL, "am_silu_bwd: bad args");
+    silu_bwd_kernel<<<grid_for(n), TB, 0, ST>>>(dy, x, dx, n); AM_LAUNCH_CHECK("silu_bwd"); return AM_OK;
+}

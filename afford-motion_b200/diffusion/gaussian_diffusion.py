@@ -347,12 +347,14 @@ class GaussianDiffusion:
         model_output = model(x_t, self._scale_timesteps(t), **model_kwargs)
         target = x_start if self.model_mean_type == ModelMeanType.START_X else noise.float()
         assert model_output.shape == target.shape == x_start.shape
-        if model_output.requires_grad:
-            raise NotImplementedError("afford-motion_b200 round 1: masked-MSE backward is not built yet")
         mask3 = x_mask.reshape(B, -1).to(th.uint8).contiguous()
         T = mask3.shape[1]
-        loss = th.empty(B, device=x_start.device)
-        ops.masked_mse(target.reshape(B, T, -1).contiguous(), model_output.float().reshape(B, T, -1).contiguous(), mask3, loss)
+        if model_output.requires_grad:  # training: differentiable masked MSE (backward kernel am_masked_mse_bwd)
+            from amb200.autograd_ops import MaskedMSEFn
+            loss = MaskedMSEFn.apply(model_output.float().reshape(B, T, -1), target.reshape(B, T, -1), mask3)
+        else:
+            loss = th.empty(B, device=x_start.device)
+            ops.masked_mse(target.reshape(B, T, -1).contiguous(), model_output.float().reshape(B, T, -1).contiguous(), mask3, loss)
         return {"mse": loss, "loss": loss}
 
 

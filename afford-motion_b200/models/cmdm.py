@@ -103,9 +103,12 @@ class CMDM(nn.Module):
         """x [bs, seq_len, motion_dim], timesteps int64 [bs] -> [bs, seq_len, motion_dim]  (cmdm.py:118-196)."""
         if not x.is_cuda:
             raise RuntimeError("afford-motion_b200: CMDM runs on CUDA (sm_100a) only — there is no CPU fallback")
-        if torch.is_grad_enabled() and self.training:
-            raise NotImplementedError("afford-motion_b200 round 1: the CMDM training (backward) path is not built yet; "
-                                      "call under torch.no_grad() / model.eval() for sampling")
+        if self.training:
+            # training path (utils/training.py:141-154): autograd graph of libamb200 kernels, batch-statistics BatchNorm,
+            # dropout, conditioning re-encoded every step
+            from amb200.cmdm_train import cmdm_forward_train
+            text = encode_text_clip(self.text_model, kwargs["c_text"], max_length=self.text_max_length, device=x.device).detach().float()
+            return cmdm_forward_train(self, x.float().contiguous(), timesteps, text, kwargs)
         cond = self.encode_condition(x.shape[1], **kwargs)
         t_dev = timesteps.to(device=x.device, dtype=torch.int32).contiguous()
         return self.engine.forward(x.float().contiguous(), t_dev, 1, cond)

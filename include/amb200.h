@@ -193,6 +193,54 @@ int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp, const flo
 int am_mha_tc_fwd(const void* qkv2, float* out, void* out2, const uint8_t* key_pad, int B, int S, int H, int hd,
                   float scale, am_stream_t stream);
 
+/* ------------------------------------------------------------------ training path (forward-with-statistics + backward)
+ * fp32 SIMT building blocks of the CMDM training step (utils/training.py:141-154 -> diffusion training_losses ->
+ * models/cmdm.py forward/backward).  Autograd graph: amb200/autograd_ops.py.  Train-mode BatchNorm1d uses batch
+ * statistics like torch (pointtransformer.py BN layers under model.train()). */
+/* C[b] = alpha * op(A[b]) * op(B[b]) + beta * C[b], row-major; batch offset = (i / bdiv) * s?1 + (i % bdiv) * s?2 */
+int am_gemm_f32(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb,
+                float beta, float* C, int ldc, int batch, int bdiv, int64_t sA1, int64_t sA2, int64_t sB1, int64_t sB2,
+                int64_t sC1, int64_t sC2, am_stream_t stream);
+int am_colsum_f32(const float* X, int ldx, float* out, int M, int N, float beta, am_stream_t stream);
+int am_gelu_fwd(const float* x, float* y, int64_t n, am_stream_t stream);
+int am_gelu_bwd(const float* dy, const float* x, float* dx, int64_t n, am_stream_t stream);
+int am_relu_bwd(const float* dy, const float* y, float* dx, int64_t n, am_stream_t stream);
+int am_silu_fwd(const float* x, float* y, int64_t n, am_stream_t stream);
+int am_silu_bwd(const float* dy, const float* x, float* dx, int64_t n, am_stream_t stream);
+int am_add_f32(const float* a, const float* b, float* y, int64_t n, int relu, am_stream_t stream);
+/* inverted dropout with a counter-based (Philox) mask addressed by (seed, site, element): the same call on the
+ * gradient is the backward pass */
+int am_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, uint32_t site, am_stream_t stream);
+/* dX of Y = LN(X (+R)); dgamma / dbeta are accumulated into (caller zeroes them) */
+int am_layernorm_bwd(const float* dY, const float* X, const float* R, const float* gamma, float* dX, float* dgamma,
+                     float* dbeta, int M, int D, float eps, am_stream_t stream);
+/* attention pieces on materialised [B*H, Sq, Sk] score buffers (training keeps the probabilities for backward) */
+int am_softmax_rows_fwd(float* S, const uint8_t* key_pad, int rows, int Sk, int rows_per_batch, float scale, am_stream_t stream);
+int am_softmax_rows_bwd(float* dP, const float* P, int rows, int Sk, float scale, am_stream_t stream);
+/* BatchNorm1d over the M rows of X [M,C]: acc = caller-zeroed [2C] double scratch */
+int am_bn_train_stats(const float* X, int M, int C, float eps, double* acc, float* mean, float* invstd, float* var_biased,
+                      am_stream_t stream);
+int am_bn_apply(const float* X, const float* mean, const float* invstd, const float* gamma, const float* beta, float* Y,
+                int M, int C, int relu, am_stream_t stream);
+int am_bn_bwd(const float* dY, const float* X, const float* Y, const float* mean, const float* invstd, const float* gamma,
+              double* acc, float* dX, float* dgamma, float* dbeta, int M, int C, int relu, am_stream_t stream);
+/* grouped point operations of PointTransformerLayer / TransitionDown with materialised [n,k,c] tensors */
+int am_scatter_add_rows(const float* src, int src_ld, int src_off, const int32_t* idx, float* dst, int64_t m, int c, am_stream_t stream);
+int am_group_rel(const float* p, const float* q, const int32_t* idx, float* rel, int64_t m, int k, am_stream_t stream);
+int am_group_cat(const float* rel, const float* x, const int32_t* idx, float* G, int64_t mk, int c, am_stream_t stream);
+int am_pt_w_fwd(const float* qkv, const int32_t* idx, const float* pr, float* w, int64_t n, int k, int c, am_stream_t stream);
+int am_pt_w_bwd(const float* dw, const int32_t* idx, float* dqkv, float* dpr, int64_t n, int k, int c, am_stream_t stream);
+int am_softmax_k_fwd(float* w, int64_t n, int k, int c8, am_stream_t stream);
+int am_softmax_k_bwd(float* dw, const float* w, int64_t n, int k, int c8, am_stream_t stream);
+int am_pt_agg_fwd(const float* qkv, const int32_t* idx, const float* pr, const float* ws, float* out, int64_t n, int k, int c, am_stream_t stream);
+int am_pt_agg_bwd(const float* dout, const float* qkv, const int32_t* idx, const float* pr, const float* ws, float* dqkv, float* dpr,
+                  float* dws, int64_t n, int k, int c, am_stream_t stream);
+int am_maxpool_k_fwd(const float* Z, float* out, int32_t* arg, int64_t m, int k, int c, am_stream_t stream);
+int am_maxpool_k_bwd(const float* dout, const int32_t* arg, float* dZ, int64_t m, int k, int c, am_stream_t stream);
+/* d/dpred of the masked MSE (gaussian_diffusion.py:815-818): gloss[b] = upstream gradient of loss[b] */
+int am_masked_mse_bwd(const float* x0, const float* pred, const uint8_t* mask, const float* gloss, float* dpred, int B, int T, int D,
+                      am_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

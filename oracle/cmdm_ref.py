@@ -35,7 +35,19 @@ def contact_tokens(sd, xyz, contact, blocks=(2, 2, 2, 2)):
 
 
 def cmdm_forward(sd, x, t, text_feat, xyz, contact, x_mask, nlayers=5, nhead=8, cont_emb=None,
-                 c_text_mask=None, c_text_erase=None, c_pc_mask=None, c_pc_erase=None, mask_motion=True):
+                 c_text_mask=None, c_text_erase=None, c_pc_mask=None, c_pc_erase=None, mask_motion=True, train=False):
+    """train=True: model.train() semantics with every dropout probability 0 (batch-statistics BatchNorm)."""
+    from . import nn_ref
+    nn_ref.TRAIN_BN = bool(train)
+    try:
+        return _cmdm_forward(sd, x, t, text_feat, xyz, contact, x_mask, nlayers, nhead, cont_emb, c_text_mask, c_text_erase, c_pc_mask,
+                             c_pc_erase, mask_motion)
+    finally:
+        nn_ref.TRAIN_BN = False
+
+
+def _cmdm_forward(sd, x, t, text_feat, xyz, contact, x_mask, nlayers, nhead, cont_emb, c_text_mask, c_text_erase, c_pc_mask, c_pc_erase,
+                  mask_motion):
     B, T, _ = x.shape
     time_emb = timestep_embed(sd, "timestep_embedder", t)  # [B,1,512]
     text_emb = text_feat.unsqueeze(1).float()

@@ -14,8 +14,17 @@ def ln(sd, name, x, eps=1e-5):
     return F.layer_norm(x, (x.shape[-1],), sd[name + ".weight"], sd[name + ".bias"], eps)
 
 
+TRAIN_BN = False  # set by oracle.cmdm_ref.cmdm_forward(train=True): BatchNorm1d uses batch statistics (model.train())
+
+
 def bn_eval(sd, name, x, eps=1e-5):
-    """BatchNorm1d in eval mode on the channel (last) dim: per-channel affine from running stats."""
+    """BatchNorm1d on the channel (last) dim.  Eval: per-channel affine from running stats.  Train (TRAIN_BN): batch
+    statistics over every other dim, biased variance (torch.nn.functional.batch_norm(training=True))."""
+    if TRAIN_BN:
+        dims = tuple(range(x.dim() - 1))
+        mean = x.mean(dim=dims)
+        var = x.var(dim=dims, unbiased=False)
+        return (x - mean) / torch.sqrt(var + eps) * sd[name + ".weight"] + sd[name + ".bias"]
     s = sd[name + ".weight"] / torch.sqrt(sd[name + ".running_var"] + eps)
     return (x - sd[name + ".running_mean"]) * s + sd[name + ".bias"]
 

@@ -77,6 +77,11 @@ def main():
     install_stubs()
     from amb200 import synth
     from oracle import pointops_ref
+    # The reference's `diffusion/` has no __init__.py (namespace package), so a regular package of the same name anywhere on
+    # sys.path would shadow it: drop this repo's drop-in packages from the path before importing the reference.
+    sys.path[:] = [p for p in sys.path if os.path.abspath(p) != os.path.join(ROOT, "afford-motion_b200")]
+    for mod in [k for k in sys.modules if k == "diffusion" or k.startswith("diffusion.") or k == "models" or k.startswith("models.")]:
+        del sys.modules[mod]
 
     import models.cdm as rcdm
     import models.cmdm as rcmdm
@@ -236,6 +241,51 @@ def main():
                 res["chain_out"] = img.numpy()
         res["x_mask"] = x_mask.numpy()
         np.savez_compressed(os.path.join(HERE, f"cmdm_b3_n{N}.npz"), **res)
+
+    # ---------------------------------------------------------------- CMDM training step (train mode, dropout p=0), B=2, N=1024
+    torch.manual_seed(0)
+    cm = rcmdm.CMDM(DictConfig(cmdm_cfg(1024)), device="cpu")
+    shapes = {k: tuple(v.shape) for k, v in cm.state_dict().items()}
+    cm.load_state_dict(synth.fill_state_dict(shapes, seed=0), strict=False)
+    cm.train()
+    for mod in cm.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+        if isinstance(mod, torch.nn.MultiheadAttention):
+            mod.dropout = 0.0
+    B, Tm, D = 2, 196, 263
+    xyz = synth.scene_points(B, 1024, seed=31, dup_frac=0.05)
+    contact = synth.contact_map(B, 1024, seed=31)
+    x0 = synth.motion_noise(B, Tm, D, seed=31)
+    x_mask = synth.motion_mask(B, Tm, seed=31)
+    x_mask[1, 100:] = True
+    text_holder["feat"] = synth.text_features(B, seed=31)
+    noise = synth.step_noise((B, Tm, D), 77)
+    tt = torch.tensor([700, 23])
+    T = 1000
+    d = SpacedDiffusion(use_timesteps=space_timesteps(T, [T]), betas=gd.get_named_beta_schedule("cosine", T),
+                        model_mean_type=gd.ModelMeanType.START_X, model_var_type=gd.ModelVarType.FIXED_SMALL,
+                        loss_type=gd.LossType.MSE, rescale_timesteps=False)
+    terms = d.training_losses(cm, x0, tt, model_kwargs=dict(c_text=["a"] * B, c_pc_xyz=xyz, c_pc_contact=contact, x_mask=x_mask), noise=noise)
+    loss = terms["loss"].mean()
+    loss.backward()
+    tr = {"loss": terms["loss"].detach().numpy(), "x_mask": x_mask.numpy(), "t": tt.numpy()}
+    norms = {}
+    for n_, p_ in cm.named_parameters():
+        if p_.grad is not None:
+            norms[n_] = float(p_.grad.norm())
+    tr["grad_names"] = np.array(sorted(norms))
+    tr["grad_norms"] = np.array([norms[k] for k in sorted(norms)])
+    for k in ("language_adapter.bias", "motion_layer.bias", "contact_encoder.enc1.0.linear.weight", "contact_encoder.enc2.0.bn.weight",
+              "contact_encoder.enc4.1.transformer2.linear_w.5.weight", "contact_encoder.enc1.1.transformer2.linear_p.0.weight",
+              "timestep_embedder.time_embed.0.bias", "self_attn_layer.layers.0.norm1.weight", "self_attn_layer.layers.4.self_attn.in_proj_bias",
+              "contact_adapter.bias"):
+        tr["grad::" + k] = dict(cm.named_parameters())[k].grad.numpy()
+    sdt = cm.state_dict()
+    for k in ("contact_encoder.enc1.0.bn.running_mean", "contact_encoder.enc1.0.bn.running_var",
+              "contact_encoder.enc3.1.transformer2.linear_w.3.running_var"):
+        tr["buf::" + k] = sdt[k].numpy()
+    np.savez_compressed(os.path.join(HERE, "cmdm_train_b2_n1024.npz"), **tr)
 
     with open(os.path.join(HERE, "state_keys.json"), "w") as f:
         json.dump(keys, f, indent=0, sort_keys=True)
