@@ -266,7 +266,14 @@ class BatchNormTrainFn(Function):
             _l.check(L().am_bn_bwd(_p(dy), _p(x), _p(y), _p(mean), _p(invstd), _p(gamma), _p(acc), _p(dx), _p(dg), _p(db), M, C, int(ctx.relu), _st()),
                      "am_bn_bwd")
         else:
-            raise NotImplementedError("SyncBatchNorm backward over ranks: next step (needs the reduce / apply halves of am_bn_bwd split)")
+            # SyncBatchNorm: local (sum dy', sum dy' xhat) -> parameter gradients are the LOCAL sums (DDP averages them over ranks,
+            # same as torch.nn.SyncBatchNorm), the input gradient uses the GLOBAL sums and the global row count
+            _l.check(L().am_bn_bwd_reduce(_p(dy), _p(x), _p(y), _p(mean), _p(invstd), _p(acc), M, C, int(ctx.relu), _st()), "am_bn_bwd_reduce")
+            db, dg = acc[:C].float(), acc[C:].float()
+            dist.all_reduce(acc)
+            scratch_g, scratch_b = torch.zeros(C, device=dy.device), torch.zeros(C, device=dy.device)
+            _l.check(L().am_bn_bwd_apply(_p(dy), _p(x), _p(y), _p(mean), _p(invstd), _p(gamma), _p(acc), _p(dx), _p(scratch_g), _p(scratch_b), M,
+                                         ctx.Mtot, C, int(ctx.relu), _st()), "am_bn_bwd_apply")
         return dx, dg, db, None, None
 
 

@@ -22,13 +22,16 @@ struct GemmG {
     int M, N, K, lda, ldb, ldc, transA, transB;
     float alpha, beta;
     int bdiv; int64_t sA1, sA2, sB1, sB2, sC1, sC2;
+    int ksplit, kchunk;  // ksplit > 1 (batch == 1 only): blockIdx.z owns K range [z*kchunk, ...), results are atomically added into C
 };
 
 __global__ void __launch_bounds__(256) gemm_general_kernel(GemmG g) {
     constexpr int BT = 64, BK = 16;
     __shared__ float As[BK][BT + 1];
     __shared__ float Bs[BK][BT + 1];
-    const int bi = blockIdx.z;
+    const int bi = g.ksplit > 1 ? 0 : blockIdx.z;
+    const int kbeg = g.ksplit > 1 ? blockIdx.z * g.kchunk : 0;
+    const int kend = g.ksplit > 1 ? min(g.K, kbeg + g.kchunk) : g.K;
     const float* A = g.A + (bi / g.bdiv) * g.sA1 + (bi % g.bdiv) * g.sA2;
     const float* B = g.B + (bi / g.bdiv) * g.sB1 + (bi % g.bdiv) * g.sB2;
     float* C = g.C + (bi / g.bdiv) * g.sC1 + (bi % g.bdiv) * g.sC2;
@@ -39,7 +42,7 @@ __global__ void __launch_bounds__(256) gemm_general_kernel(GemmG g) {
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int k0 = 0; k0 < g.K; k0 += BK) {
+    for (int k0 = kbeg; k0 < kend; k0 += BK) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             int idx = tid + i * 256;
@@ -47,13 +50,13 @@ __global__ void __launch_bounds__(256) gemm_general_kernel(GemmG g) {
             if (g.transA) { m = idx & 63; k = idx >> 6; } else { k = idx & 15; m = idx >> 4; }
             int gm = m0 + m, gk = k0 + k;
             float v = 0.f;
-            if (gm < g.M && gk < g.K) v = g.transA ? A[(int64_t)gk * g.lda + gm] : A[(int64_t)gm * g.lda + gk];
+            if (gm < g.M && gk < kend) v = g.transA ? A[(int64_t)gk * g.lda + gm] : A[(int64_t)gm * g.lda + gk];
             As[k][m] = v;
             int n;
             if (g.transB) { k = idx & 15; n = idx >> 4; } else { n = idx & 63; k = idx >> 6; }
             int gn = n0 + n; gk = k0 + k;
             v = 0.f;
-            if (gn < g.N && gk < g.K) v = g.transB ? B[(int64_t)gn * g.ldb + gk] : B[(int64_t)gk * g.ldb + gn];
+            if (gn < g.N && gk < kend) v = g.transB ? B[(int64_t)gn * g.ldb + gk] : B[(int64_t)gk * g.ldb + gn];
             Bs[k][n] = v;
         }
         __syncthreads();
@@ -79,6 +82,7 @@ __global__ void __launch_bounds__(256) gemm_general_kernel(GemmG g) {
             if (n >= g.N) continue;
             float* c = C + (int64_t)m * g.ldc + n;
             float v = g.alpha * acc[i][j];
+            if (g.ksplit > 1) { atomicAdd(c, v); continue; }
             if (g.beta != 0.f) v += g.beta * *c;
             *c = v;
         }
@@ -86,20 +90,26 @@ __global__ void __launch_bounds__(256) gemm_general_kernel(GemmG g) {
 }
 
 // out[n] = beta*out[n] + sum_m X[m][n]
-__global__ void colsum_kernel(const float* __restrict__ X, int ldx, float* __restrict__ out, int M, int N, float beta) {
+// row chunks over blockIdx.y, one atomicAdd per (CTA, column); `out` pre-scaled by the launcher
+__global__ void colsum_kernel(const float* __restrict__ X, int ldx, float* __restrict__ out, int M, int N, int rows_per_cta) {
     __shared__ float red[8][33];
     int n = blockIdx.x * 32 + (threadIdx.x & 31);
     int r = threadIdx.x >> 5;
+    int m0 = blockIdx.y * rows_per_cta, m1 = min(M, m0 + rows_per_cta);
     float s = 0.f;
     if (n < N)
-        for (int m = r; m < M; m += 8) s += X[(int64_t)m * ldx + n];
+        for (int m = m0 + r; m < m1; m += 8) s += X[(int64_t)m * ldx + n];
     red[r][threadIdx.x & 31] = s;
     __syncthreads();
     if (r == 0 && n < N) {
         float t = 0.f;
         for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x & 31];
-        out[n] = (beta != 0.f ? beta * out[n] : 0.f) + t;
+        atomicAdd(&out[n], t);
     }
+}
+__global__ void scale_vec_kernel(float* __restrict__ v, int n, float beta) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = beta == 0.f ? 0.f : v[i] * beta;
 }
 
 // ---------------------------------------------------------------- elementwise
@@ -440,15 +450,33 @@ extern "C" int am_gemm_f32(int transA, int transB, int M, int N, int K, float al
                            float* C, int ldc, int batch, int bdiv, int64_t sA1, int64_t sA2, int64_t sB1, int64_t sB2, int64_t sC1, int64_t sC2,
                            am_stream_t stream) {
     AM_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && batch > 0 && bdiv > 0, AM_EINVAL, "am_gemm_f32: bad args");
-    GemmG g{A, B, C, M, N, K, lda, ldb, ldc, transA, transB, alpha, beta, bdiv, sA1, sA2, sB1, sB2, sC1, sC2};
+    GemmG g{A, B, C, M, N, K, lda, ldb, ldc, transA, transB, alpha, beta, bdiv, sA1, sA2, sB1, sB2, sC1, sC2, 1, K};
     dim3 grid(cdiv(N, 64), cdiv(M, 64), batch);
+    // split-K for deep reductions with few output tiles (weight gradients dW = dY^T X: K = rows of the batch)
+    const int64_t tiles = (int64_t)grid.x * grid.y;
+    if (batch == 1 && beta == 0.f && ldc == N && K >= 2048 && tiles < 2 * AM_NUM_SMS) {
+        int ks = (int)((2 * AM_NUM_SMS + tiles - 1) / tiles);
+        int maxks = cdiv(K, 512);
+        if (ks > maxks) ks = maxks;
+        if (ks > 1) {
+            g.kchunk = cdiv(cdiv(K, ks), 16) * 16;
+            g.ksplit = cdiv(K, g.kchunk);
+            grid.z = g.ksplit;
+            cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, ST);
+        }
+    }
     gemm_general_kernel<<<grid, 256, 0, ST>>>(g);
     AM_LAUNCH_CHECK("gemm_f32");
     return AM_OK;
 }
 extern "C" int am_colsum_f32(const float* X, int ldx, float* out, int M, int N, float beta, am_stream_t stream) {
     AM_REQUIRE(X && out && M > 0 && N > 0, AM_EINVAL, "am_colsum_f32: bad args");
-    colsum_kernel<<<cdiv(N, 32), 256, 0, ST>>>(X, ldx, out, M, N, beta);
+    scale_vec_kernel<<<cdiv(N, 128), 128, 0, ST>>>(out, N, beta);
+    AM_LAUNCH_CHECK("colsum_scale");
+    int chunks = cdiv(M, 1024);
+    if (chunks > 4 * AM_NUM_SMS) chunks = 4 * AM_NUM_SMS;
+    int rows_per_cta = cdiv(M, chunks);
+    colsum_kernel<<<dim3(cdiv(N, 32), cdiv(M, rows_per_cta)), 256, 0, ST>>>(X, ldx, out, M, N, rows_per_cta);
     AM_LAUNCH_CHECK("colsum");
     return AM_OK;
 }
@@ -516,6 +544,25 @@ extern "C" int am_bn_bwd(const float* dY, const float* X, const float* Y, const 
     bn_bwd_reduce_kernel<<<grid, 256, sizeof(float) * 512, ST>>>(dY, X, Y, mean, invstd, M, C, relu, acc);
     AM_LAUNCH_CHECK("bn_bwd_reduce");
     bn_bwd_apply_kernel<<<grid_for((int64_t)M * C), TB, 0, ST>>>(dY, X, Y, mean, invstd, gamma, acc, dX, (int64_t)M * C, M, C, relu);
+    AM_LAUNCH_CHECK("bn_bwd_apply");
+    acc_to_float_kernel<<<cdiv(C, 128), 128, 0, ST>>>(acc, dgamma, dbeta, C);
+    AM_LAUNCH_CHECK("bn_bwd_acc");
+    return AM_OK;
+}
+// the two halves of am_bn_bwd, split so that SyncBatchNorm can all-reduce `acc` (sum dy', sum dy' xhat) across ranks between them
+extern "C" int am_bn_bwd_reduce(const float* dY, const float* X, const float* Y, const float* mean, const float* invstd, double* acc, int M, int C,
+                                int relu, am_stream_t stream) {
+    AM_REQUIRE(dY && X && mean && invstd && acc && M > 0 && C > 0 && (!relu || Y), AM_EINVAL, "am_bn_bwd_reduce: bad args");
+    int rows_per_blk = 256 / (C < 256 ? C : 256); if (rows_per_blk < 1) rows_per_blk = 1;
+    int grid = (int)(cdiv(M, rows_per_blk * 64) < AM_NUM_SMS * 8 ? cdiv(M, rows_per_blk * 64) : AM_NUM_SMS * 8);
+    bn_bwd_reduce_kernel<<<grid, 256, sizeof(float) * 512, ST>>>(dY, X, Y, mean, invstd, M, C, relu, acc);
+    AM_LAUNCH_CHECK("bn_bwd_reduce");
+    return AM_OK;
+}
+extern "C" int am_bn_bwd_apply(const float* dY, const float* X, const float* Y, const float* mean, const float* invstd, const float* gamma,
+                               const double* acc, float* dX, float* dgamma, float* dbeta, int M, int Mtotal, int C, int relu, am_stream_t stream) {
+    AM_REQUIRE(dY && X && mean && invstd && gamma && acc && dX && dgamma && dbeta && M > 0 && Mtotal >= M && C > 0, AM_EINVAL, "am_bn_bwd_apply: bad args");
+    bn_bwd_apply_kernel<<<grid_for((int64_t)M * C), TB, 0, ST>>>(dY, X, Y, mean, invstd, gamma, acc, dX, (int64_t)M * C, Mtotal, C, relu);
     AM_LAUNCH_CHECK("bn_bwd_apply");
     acc_to_float_kernel<<<cdiv(C, 128), 128, 0, ST>>>(acc, dgamma, dbeta, C);
     AM_LAUNCH_CHECK("bn_bwd_acc");

@@ -224,6 +224,13 @@ int am_bn_apply(const float* X, const float* mean, const float* invstd, const fl
                 int M, int C, int relu, am_stream_t stream);
 int am_bn_bwd(const float* dY, const float* X, const float* Y, const float* mean, const float* invstd, const float* gamma,
               double* acc, float* dX, float* dgamma, float* dbeta, int M, int C, int relu, am_stream_t stream);
+/* the two halves of am_bn_bwd: SyncBatchNorm (train_ddp.py:63) all-reduces `acc` over ranks between them; Mtotal = global rows.
+ * NOTE dgamma/dbeta written by the apply half hold the GLOBAL sums (DDP then averages parameter gradients over ranks, exactly
+ * like torch.nn.SyncBatchNorm whose weight/bias gradients are per-rank partial sums — callers divide accordingly). */
+int am_bn_bwd_reduce(const float* dY, const float* X, const float* Y, const float* mean, const float* invstd, double* acc, int M, int C,
+                     int relu, am_stream_t stream);
+int am_bn_bwd_apply(const float* dY, const float* X, const float* Y, const float* mean, const float* invstd, const float* gamma,
+                    const double* acc, float* dX, float* dgamma, float* dbeta, int M, int Mtotal, int C, int relu, am_stream_t stream);
 /* grouped point operations of PointTransformerLayer / TransitionDown with materialised [n,k,c] tensors */
 int am_scatter_add_rows(const float* src, int src_ld, int src_off, const int32_t* idx, float* dst, int64_t m, int c, am_stream_t stream);
 int am_group_rel(const float* p, const float* q, const int32_t* idx, float* rel, int64_t m, int k, am_stream_t stream);
