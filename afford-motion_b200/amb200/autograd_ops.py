@@ -415,3 +415,49 @@ def linear(x, w, b=None):
 
 def bn_train(x, bn, relu=False):
     return BatchNormTrainFn.apply(x, bn.weight, bn.bias, bn, relu)
+
+
+class MHAFn(Function):
+    """General multi-head attention core on separate q [B,Sq,C], k [B,Sk,C], v [B,Sk,Cv] (no mask):
+    softmax(q_h k_h^T * scale) (dropout) v_h, heads split along the channel dim — the Perceiver cross/self attention of
+    models/modules.py:324-381.  Batched strided GEMMs + row softmax kernels; probabilities kept for backward."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, H, scale, p_drop, seed, site):
+        q, k, v = _c(q), _c(k), _c(v)
+        B, Sq, C = q.shape
+        Sk, Cv = k.shape[1], v.shape[2]
+        c, cv = C // H, Cv // H
+        P = torch.empty(B * H, Sq, Sk, device=q.device)
+        sP = (H * Sq * Sk, Sq * Sk)
+        gemm(q, k, P, Sq, Sk, c, transB=True, lda=C, ldb=C, ldc=Sk, batch=B * H, bdiv=H, sA=(Sq * C, c), sB=(Sk * C, c), sC=sP)
+        _l.check(L().am_softmax_rows_fwd(_p(P), None, B * H * Sq, Sk, H * Sq, float(scale), _st()), "am_softmax_rows_fwd")
+        Pd = P
+        if p_drop > 0:
+            Pd = torch.empty_like(P)
+            _l.check(L().am_dropout(_p(P), _p(Pd), P.numel(), float(p_drop), seed, site, _st()), "am_dropout")
+        out = torch.empty(B, Sq, Cv, device=q.device)
+        gemm(Pd, v, out, Sq, cv, Sk, lda=Sk, ldb=Cv, ldc=Cv, batch=B * H, bdiv=H, sA=sP, sB=(Sk * Cv, cv), sC=(Sq * Cv, cv))
+        ctx.save_for_backward(q, k, v, P, Pd)
+        ctx.meta = (B, Sq, Sk, C, Cv, H, c, cv, scale, p_drop, seed, site)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, P, Pd = ctx.saved_tensors
+        B, Sq, Sk, C, Cv, H, c, cv, scale, p_drop, seed, site = ctx.meta
+        dout = _c(dout)
+        sP = (H * Sq * Sk, Sq * Sk)
+        sq, sk, sv, so = (Sq * C, c), (Sk * C, c), (Sk * Cv, cv), (Sq * Cv, cv)
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        dP = torch.empty_like(P)
+        gemm(dout, v, dP, Sq, Sk, cv, transB=True, lda=Cv, ldb=Cv, ldc=Sk, batch=B * H, bdiv=H, sA=so, sB=sv, sC=sP)       # dO V^T
+        gemm(Pd, dout, dv, Sk, cv, Sq, transA=True, lda=Sk, ldb=Cv, ldc=Cv, batch=B * H, bdiv=H, sA=sP, sB=so, sC=sv)      # dV = Pd^T dO
+        if p_drop > 0:
+            d2 = torch.empty_like(dP)
+            _l.check(L().am_dropout(_p(dP), _p(d2), dP.numel(), float(p_drop), seed, site, _st()), "am_dropout")
+            dP = d2
+        _l.check(L().am_softmax_rows_bwd(_p(dP), _p(P), B * H * Sq, Sk, float(scale), _st()), "am_softmax_rows_bwd")
+        gemm(dP, k, dq, Sq, c, Sk, lda=Sk, ldb=C, ldc=C, batch=B * H, bdiv=H, sA=sP, sB=sk, sC=sq)                          # dQ = dS K
+        gemm(dP, q, dk, Sk, c, Sq, transA=True, lda=Sk, ldb=C, ldc=C, batch=B * H, bdiv=H, sA=sP, sB=sq, sC=sk)            # dK = dS^T Q
+        return dq, dk, dv, None, None, None, None, None

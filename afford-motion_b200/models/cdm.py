@@ -95,9 +95,10 @@ class CDM(nn.Module):
         """x [bs, num_points, contact_dim], timesteps int64 [bs] -> [bs, num_points, contact_dim]  (cdm.py:474-513)."""
         if not x.is_cuda:
             raise RuntimeError("afford-motion_b200: CDM runs on CUDA (sm_100a) only — there is no CPU fallback")
-        if torch.is_grad_enabled() and self.training:
-            raise NotImplementedError("afford-motion_b200 round 1: the CDM training (backward) path is not built yet; "
-                                      "call under torch.no_grad() / model.eval() for sampling")
+        if self.training:  # autograd graph of libamb200 kernels, unfolded Perceiver, attention dropout (cdm.yaml:41,48)
+            from amb200.cdm_train import cdm_forward_train
+            text = encode_text_clip(self.text_model, kwargs["c_text"], max_length=self.text_max_length, device=x.device).detach().float()
+            return cdm_forward_train(self, x.float().contiguous(), timesteps, text, kwargs)
         cond = self.encode_condition(**kwargs)
         t_dev = timesteps.to(device=x.device, dtype=torch.int32).contiguous()
         return self.engine.forward(x.float().contiguous(), t_dev, 1, cond)

@@ -287,6 +287,35 @@ def main():
         tr["buf::" + k] = sdt[k].numpy()
     np.savez_compressed(os.path.join(HERE, "cmdm_train_b2_n1024.npz"), **tr)
 
+    # ---------------------------------------------------------------- CDM training step (train mode, dropout p=0), B=2, N=1024
+    torch.manual_seed(0)
+    cdm = rcdm.CDM(DictConfig(CDM_CFG), device="cpu")
+    shapes = {k: tuple(v.shape) for k, v in cdm.state_dict().items()}
+    cdm.load_state_dict(synth.fill_state_dict(shapes, seed=0), strict=False)
+    cdm.train()
+    for mod in cdm.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    B, N = 2, 1024
+    xyz = synth.scene_points(B, N, seed=41)
+    x0 = torch.randn(B, N, 6, generator=torch.Generator().manual_seed(41))
+    noise = synth.step_noise((B, N, 6), 78)
+    text_holder["feat"] = synth.text_features(B, seed=41)
+    tt = torch.tensor([400, 7])
+    d5 = SpacedDiffusion(use_timesteps=space_timesteps(500, [500]), betas=gd.get_named_beta_schedule("cosine", 500),
+                         model_mean_type=gd.ModelMeanType.START_X, model_var_type=gd.ModelVarType.FIXED_SMALL,
+                         loss_type=gd.LossType.MSE, rescale_timesteps=False)
+    terms = d5.training_losses(cdm, x0, tt, model_kwargs=dict(c_text=["a"] * B, c_pc_xyz=xyz, c_pc_feat=None), noise=noise)
+    terms["loss"].mean().backward()
+    tr = {"loss": terms["loss"].detach().numpy(), "t": tt.numpy()}
+    norms = {n_: float(p_.grad.norm()) for n_, p_ in cdm.named_parameters() if p_.grad is not None}
+    tr["grad_names"] = np.array(sorted(norms))
+    tr["grad_norms"] = np.array([norms[k] for k in sorted(norms)])
+    for k in ("contact_layer.weight", "contact_model.encoder_adapter.weight", "contact_model.decoder_cross_attn.0.module.attention.q_proj.bias",
+              "contact_model.encoder_cross_attn.0.module.kv_norm.weight", "timestep_embedder.time_embed.2.bias"):
+        tr["grad::" + k] = dict(cdm.named_parameters())[k].grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "cdm_train_b2_n1024.npz"), **tr)
+
     with open(os.path.join(HERE, "state_keys.json"), "w") as f:
         json.dump(keys, f, indent=0, sort_keys=True)
     print("golden fixtures written to", HERE)

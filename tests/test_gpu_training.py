@@ -193,3 +193,33 @@ def test_cmdm_training_step_matches_reference_and_oracle(golden_dir):
     opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, weight_decay=0.0)
     opt.step()
     assert all(torch.isfinite(p).all() for p in model.parameters())
+
+
+def test_cdm_training_step_matches_reference_and_oracle(golden_dir):
+    from amb200.config import cdm_model_cfg
+    from models.base import create_model_and_diffusion
+    from models.functions import set_text_feature_provider
+    from tests.test_train_oracle_cpu import oracle_cdm_train_step
+    g = np.load(os.path.join(golden_dir, "cdm_train_b2_n1024.npz"))
+    oloss, ograds, inp = oracle_cdm_train_step(golden_dir)
+    model, diff = create_model_and_diffusion(full_cfg(cdm_model_cfg(1024), steps=500), device=DEV)
+    model.load_state_dict(synth.fill_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed=0), strict=False)
+    model.to(DEV).train()
+    model.arch_cfg["encoder_dropout"] = 0.0  # the golden step ran with attention dropout 0
+    model.arch_cfg["decoder_dropout"] = 0.0
+    set_text_feature_provider(lambda raw: inp["txt"][: len(raw)])
+    try:
+        kw = dict(c_text=["a"] * 2, c_pc_xyz=inp["xyz"].to(DEV), c_pc_feat=None)
+        terms = diff.training_losses(model, inp["x0"].to(DEV), inp["t"].to(DEV), model_kwargs=kw, noise=inp["noise"].to(DEV))
+        terms["loss"].mean().backward()
+    finally:
+        set_text_feature_provider(None)
+    np.testing.assert_allclose(terms["loss"].detach().cpu().numpy(), g["loss"], rtol=5e-5)
+    grads = {n: p.grad for n, p in model.named_parameters() if p.grad is not None}
+    names = [str(n) for n in g["grad_names"]]
+    assert set(names) == set(grads)
+    np.testing.assert_allclose(np.array([float(grads[n].norm()) for n in names]), g["grad_norms"], rtol=3e-3, atol=1e-8)
+    gscale = max(float(v.norm()) for v in ograds.values())
+    for n in names:
+        a, b = grads[n].detach().cpu().double(), ograds[n].double()
+        assert ((a - b).norm() / (b.norm() + 1e-6 * gscale)).item() < 2e-2, n
