@@ -4,7 +4,8 @@
 // One persistent CTA per (batch, head): K and V of the head (bf16 hi|lo, 192 KB) are TMA-staged ONCE and stay in
 // shared memory for all ceil(S/128) query tiles; per query tile:
 //   S = Q K^T   : 3 key tiles x 3 split terms x 4 k-steps of tcgen05.mma M128 N128 K16 -> TMEM columns [0,384)
-//   softmax     : 4 warps, one query row per thread; pass 1 row max (tcgen05.ld), pass 2 per 64-key block
+//   softmax     : 8 warps in two groups (each owns every other 64-key block of all 128 rows); pass 1 row max
+//                 (tcgen05.ld) exchanged through smem, pass 2 per 64-key block
 //                 p = exp(s*scale - max) written BACK INTO THE S COLUMNS as packed bf16 (hi | lo) with tcgen05.st —
 //                 P never touches shared memory or HBM
 //   O = P V     : A operand = P from TMEM (tcgen05.mma [d], [a_tmem], b_desc), B = V tile in its natural
@@ -24,12 +25,12 @@ constexpr int QT = 128;            // queries per tile (UMMA M)
 constexpr int KT = 128;            // keys per K/V smem tile
 constexpr int NKT = 3;             // key tiles -> 384 keys max
 constexpr int TILE_BYTES = 128 * HD * 2;   // 16 KB: 128 rows x 64 bf16 (128-byte rows, SWIZZLE_128B)
-constexpr int ATT_THREADS = 256;
+constexpr int ATT_THREADS = 384;   // 4 control warps + 8 softmax warps (two per TMEM lane quadrant)
 constexpr int S_COL = 0, O_COL = 384;
 // smem: Q_hi, Q_lo, K_hi[3], K_lo[3], V_hi[3], V_lo[3]  = 14 tiles = 224 KB
 constexpr int OFF_QH = 0, OFF_QL = TILE_BYTES, OFF_KH = 2 * TILE_BYTES, OFF_KL = 5 * TILE_BYTES, OFF_VH = 8 * TILE_BYTES,
               OFF_VL = 11 * TILE_BYTES, OFF_BAR = 14 * TILE_BYTES;
-constexpr int ATT_SMEM = OFF_BAR + 256 + 1024;
+constexpr int ATT_SMEM = OFF_BAR + 256 + 1024 + 1024;  // barriers + mask bits, row max/sum exchange [2][128] fp32, alignment slack
 
 struct AttParams {
     int B, S, H;
@@ -37,6 +38,7 @@ struct AttParams {
     const uint8_t* key_pad;   // [B,S] 1 = ignore key, or NULL
     float* out;               // [B*S, H*64] fp32 or NULL
     __nv_bfloat16* out2;      // [B*S, 2*H*64] bf16 (hi | lo) or NULL
+    long long* dbg;           // optional clock64 timeline of CTA 0 (tools/att_timeline.py)
 };
 
 __device__ __forceinline__ uint32_t smem_u32a(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -99,17 +101,30 @@ __device__ __forceinline__ void tmem_ld32a(uint32_t taddr, uint32_t r[32]) {
         : "r"(taddr) : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tmem_st32a(uint32_t taddr, const uint32_t r[32]) {
+__device__ __forceinline__ void tmem_st16a(uint32_t taddr, const uint32_t r[16]) {
     asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
         ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-          "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
-          "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
-          "r"(r[30]), "r"(r[31])
+          "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// named barrier among the 256 softmax threads (barrier 0 is __syncthreads)
+__device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// (a, b) -> packed bf16x2 (a in the low half) with one cvt; the rounded values come back as floats by shifting
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+    hi = pack_bf16x2(a, b);
+    lo = pack_bf16x2(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
 }
 
 // K-major tile (Q, K): rows of 64 bf16 = 128 B, SWIZZLE_128B, 8-row groups 1024 B apart (validated by gemm_tc 64x3)
@@ -140,6 +155,7 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tm, AttParams p) {
     uint64_t* p_ready = bars + 6;   // [6] one per 64-key block
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 12);
     uint32_t* maskbits = tmem_holder + 1;  // [12] bit k of word w: key 32w+k is attendable
+    float* xchg = reinterpret_cast<float*>(maskbits + 12);  // [2][128] row max / row sum exchange between the two softmax groups
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
@@ -150,7 +166,7 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tm, AttParams p) {
     if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm)) : "memory");
     if (warp == 1 && lane == 0) {
         mbar_init_a(kv_full, 1); mbar_init_a(q_full, 1); mbar_init_a(q_empty, 1); mbar_init_a(s_full, 1); mbar_init_a(o_full, 1);
-        mbar_init_a(acc_free, 128);
+        mbar_init_a(acc_free, 256);
         for (int j = 0; j < 6; ++j) mbar_init_a(&p_ready[j], 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -172,6 +188,7 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tm, AttParams p) {
     __syncthreads();
     fence_after_a();
     const uint32_t tmem_base = *tmem_holder;
+    if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[0] = clock64();
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -196,9 +213,11 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tm, AttParams p) {
         if (lane == 0) {
             const uint32_t sb = smem_u32a(smem);
             mbar_wait_a(kv_full, 0);
+            if (p.dbg && blockIdx.x == 0) p.dbg[1] = clock64();
             for (int t = 0; t < nq; ++t) {
                 const uint32_t pt = t & 1;
                 mbar_wait_a(q_full, pt);
+                if (p.dbg && blockIdx.x == 0) p.dbg[8 + t] = clock64();
                 if (t > 0) mbar_wait_a(acc_free, (t - 1) & 1);  // S and O of the previous tile fully consumed
                 fence_after_a();
                 // ---- S = Q K^T (3-term split), key tile kt -> TMEM columns [128 kt, 128 kt + 128)
@@ -217,6 +236,7 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tm, AttParams p) {
                 }
                 umma_commit_a(s_full);
                 umma_commit_a(q_empty);
+                if (p.dbg && blockIdx.x == 0) p.dbg[16 + t] = clock64();
                 // ---- O = P V per 64-key block, P (bf16 hi | lo) read from TMEM where the softmax warps stored it
                 for (int j = 0; j < nblk; ++j) {
                     mbar_wait_a(&p_ready[j], pt);
@@ -232,11 +252,14 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tm, AttParams p) {
                     }
                 }
                 umma_commit_a(o_full);
+                if (p.dbg && blockIdx.x == 0) p.dbg[24 + t] = clock64();
             }
         }
     } else if (warp >= 4) {
-        // ===================== softmax + epilogue: one query row per thread =====================
-        const int q4 = warp & 3;
+        // ===================== softmax + epilogue =====================
+        // Two groups of 4 warps share every query row (thread (q4, lane) of both groups owns row 32 q4 + lane): group g
+        // handles the 64-key blocks j = g, g+2, g+4 (row max / exp / P write-back) and the output columns [32 g, 32 g + 32).
+        const int q4 = warp & 3, grp = (warp - 4) >> 2;
         const int r = q4 * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16);
         for (int t = 0; t < nq; ++t) {
@@ -244,86 +267,101 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tm, AttParams p) {
             const int qi = t * QT + r;
             mbar_wait_a(s_full, pt);
             fence_after_a();
-            // pass 1: row max of the scaled scores over attendable keys
+            if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) p.dbg[32 + t] = clock64();
+            // pass 1: row max of the scaled scores over attendable keys (own blocks), then exchange with the other group
             float mx = -CUDART_INF_F;
-            for (int c = 0; c < 2 * nblk; ++c) {
-                uint32_t v[32];
-                tmem_ld32a(lane_addr + S_COL + c * 32, v);
-                const uint32_t mb = maskbits[c];
+            for (int j = grp; j < nblk; j += 2) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if ((mb >> j) & 1u) mx = fmaxf(mx, __uint_as_float(v[j]) * p.scale);
+                for (int hlf = 0; hlf < 2; ++hlf) {
+                    uint32_t v[32];
+                    tmem_ld32a(lane_addr + S_COL + j * 64 + hlf * 32, v);
+                    const uint32_t mb = maskbits[2 * j + hlf];
+                    if (mb == 0xffffffffu) {  // warp-uniform fast path: every key of the chunk attendable
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(v[c]));
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c)
+                            if ((mb >> c) & 1u) mx = fmaxf(mx, __uint_as_float(v[c]));
+                    }
+                }
             }
+            xchg[grp * 128 + r] = mx;  // max of the RAW scores (scale > 0 commutes with max)
+            softmax_bar();
+            mx = fmaxf(mx, xchg[(grp ^ 1) * 128 + r]);
+            softmax_bar();  // xchg is reused for the row sums below
+            const float sc2 = p.scale * 1.4426950408889634f;  // exp(s*scale - max*scale) = 2^(s*sc2 - mx2)
+            const float mx2 = mx * sc2;
+            if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) p.dbg[40 + t] = clock64();
             // pass 2: p = exp(s - max) -> packed bf16 (hi | lo) back into the block's own S columns
             float sum = 0.f;
-            for (int j = 0; j < nblk; ++j) {
-                uint32_t v0[32], v1[32], ph[32], pl[32];
+            for (int j = grp; j < nblk; j += 2) {
+                uint32_t v0[32], v1[32];
                 tmem_ld32a(lane_addr + S_COL + j * 64, v0);
                 tmem_ld32a(lane_addr + S_COL + j * 64 + 32, v1);
-                const uint32_t m0 = maskbits[2 * j], m1 = maskbits[2 * j + 1];
 #pragma unroll
-                for (int c = 0; c < 32; c += 2) {
-                    float e[4];
-                    e[0] = ((m0 >> c) & 1u) ? __expf(__uint_as_float(v0[c]) * p.scale - mx) : 0.f;
-                    e[1] = ((m0 >> (c + 1)) & 1u) ? __expf(__uint_as_float(v0[c + 1]) * p.scale - mx) : 0.f;
-                    e[2] = ((m1 >> c) & 1u) ? __expf(__uint_as_float(v1[c]) * p.scale - mx) : 0.f;
-                    e[3] = ((m1 >> (c + 1)) & 1u) ? __expf(__uint_as_float(v1[c + 1]) * p.scale - mx) : 0.f;
-                    sum += (e[0] + e[1]) + (e[2] + e[3]);
-                    __nv_bfloat16 h0 = __float2bfloat16_rn(e[0]), h1 = __float2bfloat16_rn(e[1]), h2 = __float2bfloat16_rn(e[2]), h3 = __float2bfloat16_rn(e[3]);
-                    __nv_bfloat16 l0 = __float2bfloat16_rn(e[0] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(e[1] - __bfloat162float(h1));
-                    __nv_bfloat16 l2 = __float2bfloat16_rn(e[2] - __bfloat162float(h2)), l3 = __float2bfloat16_rn(e[3] - __bfloat162float(h3));
-                    // keys 64j + c, c+1 -> word c/2 ; keys 64j + 32 + c, c+1 -> word 16 + c/2   (element 2w low half, 2w+1 high half)
-                    ph[c / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                    ph[16 + c / 2] = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
-                    pl[c / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-                    pl[16 + c / 2] = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+                for (int hlf = 0; hlf < 2; ++hlf) {
+                    const uint32_t* v = hlf ? v1 : v0;
+                    const uint32_t mb = maskbits[2 * j + hlf];
+                    uint32_t ph[16], pl[16];
+                    if (mb == 0xffffffffu) {
+#pragma unroll
+                        for (int c = 0; c < 32; c += 2) {
+                            const float e0 = ex2_approx(fmaf(__uint_as_float(v[c]), sc2, -mx2));
+                            const float e1 = ex2_approx(fmaf(__uint_as_float(v[c + 1]), sc2, -mx2));
+                            sum += e0 + e1;
+                            split_pair(e0, e1, ph[c / 2], pl[c / 2]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 32; c += 2) {
+                            const float e0 = ((mb >> c) & 1u) ? ex2_approx(fmaf(__uint_as_float(v[c]), sc2, -mx2)) : 0.f;
+                            const float e1 = ((mb >> (c + 1)) & 1u) ? ex2_approx(fmaf(__uint_as_float(v[c + 1]), sc2, -mx2)) : 0.f;
+                            sum += e0 + e1;
+                            split_pair(e0, e1, ph[c / 2], pl[c / 2]);
+                        }
+                    }
+                    // keys 64j + 32 hlf + (2w, 2w+1) -> P_hi word 16 hlf + w (columns [64j, 64j+32)), P_lo 32 columns further
+                    tmem_st16a(lane_addr + S_COL + j * 64 + hlf * 16, ph);
+                    tmem_st16a(lane_addr + S_COL + j * 64 + 32 + hlf * 16, pl);
                 }
-                tmem_st32a(lane_addr + S_COL + j * 64, ph);        // P_hi: 64 keys = 32 packed columns
-                tmem_st32a(lane_addr + S_COL + j * 64 + 32, pl);   // P_lo
+                tmem_wait_st();
                 fence_before_a();
                 mbar_arrive_a(&p_ready[j]);
             }
-            // epilogue: O / rowsum
+            if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) p.dbg[48 + t] = clock64();
+            xchg[grp * 128 + r] = sum;
+            softmax_bar();
+            sum += xchg[(grp ^ 1) * 128 + r];
+            // epilogue: this group's 32 output columns of O / rowsum
             mbar_wait_a(o_full, pt);
             fence_after_a();
-            uint32_t o0[32], o1[32];
-            tmem_ld32a(lane_addr + O_COL, o0);
-            tmem_ld32a(lane_addr + O_COL + 32, o1);
+            if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) p.dbg[56 + t] = clock64();
+            uint32_t o0[32];
+            tmem_ld32a(lane_addr + O_COL + grp * 32, o0);
             fence_before_a();
             mbar_arrive_a(acc_free);  // S / O columns may be overwritten by the next query tile
+            softmax_bar();            // xchg free for the next tile
             if (qi < S) {
                 const float inv = 1.0f / sum;
                 const int64_t row = (int64_t)b * S + qi;
                 if (p.out) {
-                    float* dst = p.out + row * D + h * HD;
+                    float* dst = p.out + row * D + h * HD + grp * 32;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
+                    for (int j = 0; j < 32; j += 4)
                         *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(o0[j]) * inv, __uint_as_float(o0[j + 1]) * inv,
                                                                           __uint_as_float(o0[j + 2]) * inv, __uint_as_float(o0[j + 3]) * inv);
-                        *reinterpret_cast<float4*>(dst + 32 + j) = make_float4(__uint_as_float(o1[j]) * inv, __uint_as_float(o1[j + 1]) * inv,
-                                                                               __uint_as_float(o1[j + 2]) * inv, __uint_as_float(o1[j + 3]) * inv);
-                    }
                 }
                 if (p.out2) {
-                    __nv_bfloat16* hi = p.out2 + row * (2 * (int64_t)D) + h * HD;
+                    __nv_bfloat16* hi = p.out2 + row * (2 * (int64_t)D) + h * HD + grp * 32;
                     __nv_bfloat16* lo = hi + D;
+                    uint32_t wh[16], wl[16];
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        const uint32_t* o = half ? o1 : o0;
-                        uint32_t wh[16], wl[16];
+                    for (int j = 0; j < 32; j += 2) split_pair(__uint_as_float(o0[j]) * inv, __uint_as_float(o0[j + 1]) * inv, wh[j / 2], wl[j / 2]);
 #pragma unroll
-                        for (int j = 0; j < 32; j += 2) {
-                            float x0 = __uint_as_float(o[j]) * inv, x1 = __uint_as_float(o[j + 1]) * inv;
-                            __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-                            __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
-                            wh[j / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                            wl[j / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-                        }
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            *reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(hi + half * 32) + j) = make_uint4(wh[j], wh[j + 1], wh[j + 2], wh[j + 3]);
-                            *reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(lo + half * 32) + j) = make_uint4(wl[j], wl[j + 1], wl[j + 2], wl[j + 3]);
-                        }
+                    for (int j = 0; j < 16; j += 4) {
+                        *reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(hi) + j) = make_uint4(wh[j], wh[j + 1], wh[j + 2], wh[j + 3]);
+                        *reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(lo) + j) = make_uint4(wl[j], wl[j + 1], wl[j + 2], wl[j + 3]);
                     }
                 }
             }
@@ -339,6 +377,9 @@ typedef CUresult (*EncodeTiledFnA)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 }  // namespace
+
+static long long* g_att_dbg = nullptr;
+extern "C" void am_att_set_debug_(void* buf) { g_att_dbg = reinterpret_cast<long long*>(buf); }  // debug hook, not in the public header
 
 extern "C" int am_mha_tc_fwd(const void* qkv2, float* out, void* out2, const uint8_t* key_pad, int B, int S, int H, int hd, float scale,
                              am_stream_t stream) {
@@ -376,7 +417,7 @@ extern "C" int am_mha_tc_fwd(const void* qkv2, float* out, void* out2, const uin
         }
         attr = true;
     }
-    AttParams p{B, S, H, scale, key_pad, out, reinterpret_cast<__nv_bfloat16*>(out2)};
+    AttParams p{B, S, H, scale, key_pad, out, reinterpret_cast<__nv_bfloat16*>(out2), g_att_dbg};
     mha_tc_kernel<<<B * H, ATT_THREADS, ATT_SMEM, as_stream(stream)>>>(tm, p);
     AM_LAUNCH_CHECK("mha_tc_fwd");
     return AM_OK;
