@@ -52,6 +52,57 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     }
 }
 
+
+// Vectorised variant for D % 128 == 0 and 16-byte aligned rows: every lane owns NV float4 chunks (chunk c = lane + 32 i),
+// 128-bit loads / stores, bf16 (hi | lo) written as 8-byte pairs.
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ R, int ldr,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            float* __restrict__ Y, int ldy, int M, int D, float eps,
+                                                            __nv_bfloat16* __restrict__ Y2, int Np2) {
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    int lane = threadIdx.x & 31;
+    const float4* x4 = reinterpret_cast<const float4*>(X + (int64_t)row * ldx);
+    const float4* r4 = R ? reinterpret_cast<const float4*>(R + (int64_t)row * ldr) : nullptr;
+    float4 v[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        float4 t = x4[lane + 32 * i];
+        if (r4) { float4 u = r4[lane + 32 * i]; t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
+        v[i] = t; s += (t.x + t.y) + (t.z + t.w);
+    }
+    const float mean = warp_sum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        const float4 g = g4[c], b = b4[c];
+        float4 o;
+        o.x = (v[i].x - mean) * rstd * g.x + b.x; o.y = (v[i].y - mean) * rstd * g.y + b.y;
+        o.z = (v[i].z - mean) * rstd * g.z + b.z; o.w = (v[i].w - mean) * rstd * g.w + b.w;
+        if (Y) reinterpret_cast<float4*>(Y + (int64_t)row * ldy)[c] = o;
+        if (Y2) {
+            __nv_bfloat162 h01 = __floats2bfloat162_rn(o.x, o.y), h23 = __floats2bfloat162_rn(o.z, o.w);
+            uint32_t u01 = *reinterpret_cast<uint32_t*>(&h01), u23 = *reinterpret_cast<uint32_t*>(&h23);
+            __nv_bfloat162 l01 = __floats2bfloat162_rn(o.x - __uint_as_float(u01 << 16), o.y - __uint_as_float(u01 & 0xffff0000u));
+            __nv_bfloat162 l23 = __floats2bfloat162_rn(o.z - __uint_as_float(u23 << 16), o.w - __uint_as_float(u23 & 0xffff0000u));
+            uint2* hi = reinterpret_cast<uint2*>(Y2 + (int64_t)row * 2 * Np2) + c;
+            hi[0] = make_uint2(u01, u23);
+            hi[Np2 / 4] = make_uint2(*reinterpret_cast<uint32_t*>(&l01), *reinterpret_cast<uint32_t*>(&l23));
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int am_layernorm(const float* X, int ldx, const float* R, int ldr, const float* gamma, const float* beta, float* Y, int ldy,
@@ -61,6 +112,21 @@ extern "C" int am_layernorm(const float* X, int ldx, const float* R, int ldr, co
     AM_REQUIRE(!Y2 || (Np2 >= D && Np2 % 32 == 0 && Np2 <= 1024), AM_EINVAL, "am_layernorm: bad Np2");
     __nv_bfloat16* y2 = reinterpret_cast<__nv_bfloat16*>(Y2);
     int grid = cdiv(M, 8);
+    auto a16 = [](const void* p_) { return (reinterpret_cast<uintptr_t>(p_) & 15u) == 0; };
+    const bool vec = (D % 128 == 0) && D <= 1024 && a16(X) && (ldx % 4 == 0) && (!R || (a16(R) && ldr % 4 == 0)) && a16(gamma) && a16(beta) &&
+                     (!Y || (a16(Y) && ldy % 4 == 0)) && (!Y2 || (a16(Y2) && Np2 == D));
+    if (vec) {
+        switch (D / 128) {
+            case 1: layernorm_vec_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2); break;
+            case 2: layernorm_vec_kernel<2><<<grid, 256, 0, as_stream(stream)>>>(X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2); break;
+            case 4: layernorm_vec_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2); break;
+            case 8: layernorm_vec_kernel<8><<<grid, 256, 0, as_stream(stream)>>>(X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2); break;
+            default: goto scalar_path;
+        }
+        AM_LAUNCH_CHECK("layernorm");
+        return AM_OK;
+    }
+scalar_path:
     if (D <= 256) layernorm_kernel<8><<<grid, 256, 0, as_stream(stream)>>>(X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2);
     else if (D <= 512) layernorm_kernel<16><<<grid, 256, 0, as_stream(stream)>>>(X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2);
     else layernorm_kernel<32><<<grid, 256, 0, as_stream(stream)>>>(X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2);
