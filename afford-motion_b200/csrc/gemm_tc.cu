@@ -395,6 +395,61 @@ __device__ __forceinline__ void epilogue_tile_fast(const TcParams& p, uint32_t t
     }
 }
 
+// TMA-store epilogue (MODE 3, the bf16 (hi|lo)-only outputs of in_proj / FFN1).  Measured: LSU global stores of the
+// epilogue throttle the main loop (12.6K -> 17K cycles per 128x256 tile) and cost 6K of the epilogue's 10K cycles,
+// whatever their cache policy; handing the writes to the TMA engine removes the LSU from the output path entirely:
+//   tcgen05.ld (lane = row) -> bias / activation -> pack bf16 hi / lo -> st.shared.v4 into two 32x32 bf16 tiles laid out
+//   SWIZZLE_64B (conflict-free for one-row-per-lane writes) -> fence.proxy.async -> cp.async.bulk.tensor store (hi, lo).
+// No transpose staging and no shared-memory reads at all.  OOB rows (m >= M) are clipped by the tensor map.
+template <int ACT, int NCOLS>
+__device__ __forceinline__ void epilogue_tile_tma(const TcParams& p, const CUtensorMap* tmY, uint32_t tmem_tile, int m0, int n0, int q, int half,
+                                                  int lane, uint32_t out_u32 /* this warp's 4 KB: hi tile | lo tile */) {
+    const int m_base = m0 + q * 32;
+#pragma unroll 1
+    for (int blk = 0; blk < NCOLS / 64; ++blk) {
+        const int col0 = half * (NCOLS / 2) + blk * 32;
+        const int n = n0 + col0;
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            uint32_t v[16];
+            tmem_ld16(tmem_tile + ((uint32_t)(q * 32) << 16) + (uint32_t)(col0 + g * 16), v);
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + g * 16 + j));
+                const float x0 = act_ct<ACT>(__uint_as_float(v[j]) + b4.x), x1 = act_ct<ACT>(__uint_as_float(v[j + 1]) + b4.y);
+                const float x2 = act_ct<ACT>(__uint_as_float(v[j + 2]) + b4.z), x3 = act_ct<ACT>(__uint_as_float(v[j + 3]) + b4.w);
+                __nv_bfloat162 h01 = __floats2bfloat162_rn(x0, x1), h23 = __floats2bfloat162_rn(x2, x3);
+                const uint32_t u01 = *reinterpret_cast<uint32_t*>(&h01), u23 = *reinterpret_cast<uint32_t*>(&h23);
+                __nv_bfloat162 l01 = __floats2bfloat162_rn(x0 - __uint_as_float(u01 << 16), x1 - __uint_as_float(u01 & 0xffff0000u));
+                __nv_bfloat162 l23 = __floats2bfloat162_rn(x2 - __uint_as_float(u23 << 16), x3 - __uint_as_float(u23 & 0xffff0000u));
+                hi[g * 8 + j / 2] = u01; hi[g * 8 + j / 2 + 1] = u23;
+                lo[g * 8 + j / 2] = *reinterpret_cast<uint32_t*>(&l01); lo[g * 8 + j / 2 + 1] = *reinterpret_cast<uint32_t*>(&l23);
+            }
+        }
+        // previous block's bulk stores must have finished READING this warp's staging tiles
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+        // row = lane, 64-byte rows, 16-byte chunk c stored at chunk c ^ ((row >> 1) & 3)   (SWIZZLE_64B)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint32_t a = out_u32 + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(hi[4 * c]), "r"(hi[4 * c + 1]), "r"(hi[4 * c + 2]), "r"(hi[4 * c + 3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + 2048), "r"(lo[4 * c]), "r"(lo[4 * c + 1]), "r"(lo[4 * c + 2]), "r"(lo[4 * c + 3]) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the async (TMA) proxy
+        __syncwarp();
+        if (lane == 0 && m_base < p.M && n < p.N) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                         ::"l"(reinterpret_cast<uint64_t>(tmY)), "r"(out_u32), "r"(n), "r"(m_base) : "memory");
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                         ::"l"(reinterpret_cast<uint64_t>(tmY)), "r"(out_u32 + 2048), "r"(p.Np2 + n), "r"(m_base) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+}
+
 template <int BK, int STAGES, int MINB, int ACT>
 __global__ void __launch_bounds__(TC_THREADS, MINB)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
@@ -492,8 +547,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // double-buffered in TMEM (2 x BN_ columns) so the epilogue of tile i overlaps the main loop of tile i+1.
 template <int BN_, int NST, int ACT, int MODE>
 __global__ void __launch_bounds__(TCP_THREADS, 1)
-gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p, int n_tiles,
-                          int total_tiles) {
+gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                          const __grid_constant__ CUtensorMap tmY, TcParams p, int n_tiles, int total_tiles) {
     constexpr int BK = 32;
     constexpr int A_SUB = BM * BK * 2;          // 8 KB
     constexpr int B_SUB = BN_ * BK * 2;         // 8 / 16 KB
@@ -506,7 +561,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     uint64_t* tmem_full = empty + NST;     // [2]
     uint64_t* tmem_empty = tmem_full + 2;  // [2]
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    float* stage_buf = reinterpret_cast<float*>(smem + NST * STAGE_BYTES + 256);  // 8 warps x 32 x 32 fp32 (epilogue transpose)
+    float* stage_buf = reinterpret_cast<float*>(smem + NST * STAGE_BYTES + 1024);  // 8 warps x 4 KB (epilogue transpose / TMA-store tiles), 1024-aligned
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = p.Kp / BK;
@@ -591,12 +646,14 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             mbar_wait(&tmem_full[ab], (it >> 1) & 1);
             tc_fence_after();
             if (dbg && threadIdx.x == 0 && it < 16) p.dbg[40 + it] = clock64();
-            if (MODE == 0) epilogue_tile_coalesced<ACT, BN_>(p, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane, stage_buf + warp * (32 * 32));
+            if (MODE == 3) epilogue_tile_tma<ACT, BN_>(p, &tmY, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane, smem_u32(stage_buf + warp * (32 * 32)));
+            else if (MODE == 0) epilogue_tile_coalesced<ACT, BN_>(p, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane, stage_buf + warp * (32 * 32));
             else epilogue_tile_fast<ACT, BN_, MODE>(p, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane, smem_u32(stage_buf + warp * (32 * 32)));
             tc_fence_before();
             mbar_arrive(&tmem_empty[ab]);
             if (dbg && threadIdx.x == 0 && it < 16) p.dbg[72 + it] = clock64();
         }
+        if (MODE == 3 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all bulk stores of this warp complete before exit
     }
     tc_fence_before();
     __syncthreads();
@@ -695,7 +752,7 @@ extern "C" int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp
         cudaStream_t st = as_stream(stream);
 #define AM_TCP_LAUNCH(BN_, NST_, ACT_, MODE_)                                                                                   \
     do {                                                                                                                        \
-        constexpr int smem_ = NST_ * (2 * BM * 32 * 2 + 2 * BN_ * 32 * 2) + 1024 + 256 + 8 * 32 * 32 * 4;                       \
+        constexpr int smem_ = NST_ * (2 * BM * 32 * 2 + 2 * BN_ * 32 * 2) + 1024 + 1024 + 8 * 32 * 32 * 4;                       \
         static bool attr_ = false;                                                                                              \
         if (!attr_) {                                                                                                           \
             if (cudaFuncSetAttribute(gemm_tc_persistent_kernel<BN_, NST_, ACT_, MODE_>,                                         \
@@ -705,18 +762,33 @@ extern "C" int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp
             }                                                                                                                   \
             attr_ = true;                                                                                                       \
         }                                                                                                                       \
-        gemm_tc_persistent_kernel<BN_, NST_, ACT_, MODE_><<<grid, TCP_THREADS, smem_, st>>>(tmA, tmB, p, nt, total);              \
+        gemm_tc_persistent_kernel<BN_, NST_, ACT_, MODE_><<<grid, TCP_THREADS, smem_, st>>>(tmA, tmB, tmY, p, nt, total);              \
     } while (0)
         // epilogue mode: 1 / 2 = specialised fast paths of the big trunk GEMMs, 0 = general
         const int a15 = act & 15;
         const bool plain = yin_g == 0 && res_mod == 0 && (N % bn) == 0 && !(act & AM_ACT_AFTER_RES) &&
                            (!bias || (reinterpret_cast<uintptr_t>(bias) & 15u) == 0);
         int mode = 0;
+        CUtensorMap tmY = tmA;  // placeholder unless the TMA-store epilogue is selected
         if (plain && Y2 && !Y && !residual && Np2 == N && (N % 4) == 0 && (a15 == AM_ACT_NONE || a15 == AM_ACT_GELU)) mode = 1;
+        static int lsu_epi = -1;
+        if (lsu_epi < 0) { const char* e = getenv("AMB200_TC_EPI"); lsu_epi = (e && !strcmp(e, "lsu")) ? 1 : 0; }
+        if (mode == 1 && !lsu_epi && (N % 32) == 0) {
+            // output tensor map: Y2 [M, 2*Np2] bf16, box 32 cols x 32 rows, SWIZZLE_64B
+            EncodeTiledFn enc = get_encode();
+            cuuint64_t gdim[2] = {(cuuint64_t)2 * Np2, (cuuint64_t)M};
+            cuuint64_t gstr[1] = {(cuuint64_t)2 * Np2 * 2};
+            cuuint32_t box[2] = {32, 32};
+            cuuint32_t estr[2] = {1, 1};
+            if (enc && enc(&tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Y2, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                           CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) mode = 3;
+        }
         if (plain && Y && !Y2 && (a15 == AM_ACT_NONE || a15 == AM_ACT_GELU) && (ldy % 4) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15u) == 0 &&
             (!residual || ((ldr % 4) == 0 && (reinterpret_cast<uintptr_t>(residual) & 15u) == 0))) mode = 2;
 #define AM_TCP_BY_MODE(BN_, NST_)                                                                  \
-    if (mode == 1 && a15 == AM_ACT_GELU) AM_TCP_LAUNCH(BN_, NST_, AM_ACT_GELU, 1);                  \
+    if (mode == 3 && a15 == AM_ACT_GELU) AM_TCP_LAUNCH(BN_, NST_, AM_ACT_GELU, 3);                  \
+    else if (mode == 3) AM_TCP_LAUNCH(BN_, NST_, AM_ACT_NONE, 3);                                   \
+    else if (mode == 1 && a15 == AM_ACT_GELU) AM_TCP_LAUNCH(BN_, NST_, AM_ACT_GELU, 1);             \
     else if (mode == 1) AM_TCP_LAUNCH(BN_, NST_, AM_ACT_NONE, 1);                                   \
     else if (mode == 2 && a15 == AM_ACT_GELU) AM_TCP_LAUNCH(BN_, NST_, AM_ACT_GELU, 2);             \
     else if (mode == 2) AM_TCP_LAUNCH(BN_, NST_, AM_ACT_NONE, 2);                                   \
