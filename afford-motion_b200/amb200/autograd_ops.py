@@ -42,17 +42,38 @@ def gemm(A, B, C, M, N, K, transA=False, transB=False, alpha=1.0, beta=0.0, lda=
     return C
 
 
+def _tsplit(x2, M, K):
+    """bf16 (hi|lo) of x2^T: [K, 2*Mp]."""
+    Mp = _ops.pad32(M)
+    out = torch.empty(K, 2 * Mp, dtype=torch.bfloat16, device=x2.device)
+    _l.check(L().am_transpose_split_bf16(_p(x2), x2.stride(0), _p(out), Mp, M, K, _st()), "am_transpose_split_bf16")
+    return out, Mp
+
+
+def _use_tc(M, N, K):
+    """Large trunk layers go to the tcgen05 GEMM (3-term bf16 split, fp32 accumulate); small / odd shapes stay SIMT."""
+    return _TC_TRAIN and M >= 2048 and N >= 32 and K >= 32 and N % 4 == 0 and K % 4 == 0
+
+
+import os as _os
+_TC_TRAIN = _os.environ.get("AMB200_TRAIN_GEMM", "tc") == "tc"
+
+
 class LinearFn(Function):
     """y = x W^T (+ b) on the last dim; x [..., K], W [N, K]."""
 
     @staticmethod
-    def forward(ctx, x, w, b):
+    def forward(ctx, x, w, b, tc=False):
         x2 = _c(x).view(-1, x.shape[-1])
         w = _c(w)
         M, K = x2.shape
         N = w.shape[0]
         y = torch.empty(M, N, device=x.device)
-        _ops.linear(x2, w, y, M, N, K, bias=None if b is None else _c(b))  # fp32 SIMT GEMM with the bias fused in the epilogue
+        ctx.tc = tc = bool(tc) and _use_tc(M, N, K)
+        if tc:
+            _ops.linear_tc(_ops.split_bf16(x2, M, K), _ops.split_bf16(w, N, K), M, N, _ops.pad32(K), y=y, bias=None if b is None else _c(b))
+        else:
+            _ops.linear(x2, w, y, M, N, K, bias=None if b is None else _c(b))  # fp32 SIMT GEMM with the bias fused in the epilogue
         ctx.save_for_backward(x2, w)
         ctx.has_bias = b is not None
         ctx.xshape = x.shape
@@ -65,17 +86,27 @@ class LinearFn(Function):
         N = w.shape[0]
         dy2 = _c(dy).view(M, N)
         dx = dw = db = None
+        tc = ctx.tc
         if ctx.needs_input_grad[0]:
             dx = torch.empty(M, K, device=dy.device)
-            gemm(dy2, w, dx, M, K, N)  # dX = dY W
+            if tc:  # dX = dY W : A = dY (K-major along N), B = W^T (rows = K_in, K-major along N)
+                wt2, Np = _tsplit(w, N, K)
+                _ops.linear_tc(_ops.split_bf16(dy2, M, N), wt2, M, K, Np, y=dx)
+            else:
+                gemm(dy2, w, dx, M, K, N)
             dx = dx.view(ctx.xshape)
         if ctx.needs_input_grad[1]:
             dw = torch.empty(N, K, device=dy.device)
-            gemm(dy2, x2, dw, N, K, M, transA=True)  # dW = dY^T X
+            if tc:  # dW = dY^T X : both operands K-major along the M batch rows
+                dyt2, Mp = _tsplit(dy2, M, N)
+                xt2, _ = _tsplit(x2, M, K)
+                _ops.linear_tc(dyt2, xt2, N, K, Mp, y=dw)
+            else:
+                gemm(dy2, x2, dw, N, K, M, transA=True)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = torch.empty(N, device=dy.device)
             _l.check(L().am_colsum_f32(_p(dy2), N, _p(db), M, N, 0.0, _st()), "am_colsum_f32")
-        return dx, dw, db
+        return dx, dw, db, None
 
 
 def _unary(fwd, bwd, name):
@@ -409,8 +440,10 @@ class MaskedMSEFn(Function):
 
 
 # ---- functional helpers
-def linear(x, w, b=None):
-    return LinearFn.apply(x, w, b)
+def linear(x, w, b=None, tc=False):
+    """tc=True: large layers run on the tcgen05 GEMM (3-term bf16 split, ~1e-5 relative); used by the LayerNorm trunks.  The
+    BatchNorm scene encoder keeps fp32 SIMT GEMMs: its deep stages normalise over a handful of points and amplify GEMM noise."""
+    return LinearFn.apply(x, w, b, tc)
 
 
 def bn_train(x, bn, relu=False):

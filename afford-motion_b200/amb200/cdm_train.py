@@ -13,19 +13,19 @@ def _seed() -> int:
 def _mlp(mlp, x):
     """modules.py:651-661: LN -> Linear -> GELU -> Linear."""
     h = A.LayerNormFn.apply(x, mlp[0].weight, mlp[0].bias, mlp[0].eps)
-    h = A.GeluFn.apply(A.linear(h, mlp[1].weight, mlp[1].bias))
-    return A.linear(h, mlp[3].weight, mlp[3].bias)
+    h = A.GeluFn.apply(A.linear(h, mlp[1].weight, mlp[1].bias, tc=True))
+    return A.linear(h, mlp[3].weight, mlp[3].bias, tc=True)
 
 
 def _mha(att, xq, xkv, p_drop, seed, site):
     """modules.py:324-381: q *= c_head^-0.5 (folded into the score scale), no mask / rotary / cache."""
     H = att.num_heads
-    q = A.linear(xq, att.q_proj.weight, att.q_proj.bias)
-    k = A.linear(xkv, att.k_proj.weight, att.k_proj.bias)
-    v = A.linear(xkv, att.v_proj.weight, att.v_proj.bias)
+    q = A.linear(xq, att.q_proj.weight, att.q_proj.bias, tc=True)
+    k = A.linear(xkv, att.k_proj.weight, att.k_proj.bias, tc=True)
+    v = A.linear(xkv, att.v_proj.weight, att.v_proj.bias, tc=True)
     c = q.shape[-1] // H
     o = A.MHAFn.apply(q, k, v, H, c ** -0.5, p_drop, seed, site)
-    return A.linear(o, att.o_proj.weight, att.o_proj.bias)
+    return A.linear(o, att.o_proj.weight, att.o_proj.bias, tc=True)
 
 
 def _cross_layer(layer, xq, xkv, p_drop, seed, site):
@@ -50,19 +50,19 @@ def cdm_forward_train(m, x, timesteps, text_feat, kwargs):
     seed = _seed()
     te = m.timestep_embedder
     h = te.pe[timesteps.long()]
-    h = A.SiluFn.apply(A.linear(h, te.time_embed[0].weight, te.time_embed[0].bias))
-    time_emb = A.linear(h, te.time_embed[2].weight, te.time_embed[2].bias)          # [B,1,128]
+    h = A.SiluFn.apply(A.linear(h, te.time_embed[0].weight, te.time_embed[0].bias, tc=True))
+    time_emb = A.linear(h, te.time_embed[2].weight, te.time_embed[2].bias, tc=True)          # [B,1,128]
     text = text_feat.unsqueeze(1).float()
     u = x
     if m.point_feat_dim > 0:
         u = torch.cat([u, kwargs["c_pc_feat"].float()], dim=-1)
     u = torch.cat([u, kwargs["c_pc_xyz"].float()], dim=-1).contiguous()               # cdm.py:167-171
-    enc_kv = A.linear(u, cm.encoder_adapter.weight, cm.encoder_adapter.bias)         # [B,N,256]
-    L = torch.cat([A.linear(text, cm.language_adapter.weight, cm.language_adapter.bias),
-                   A.linear(time_emb, cm.time_embedding_adapter.weight, cm.time_embedding_adapter.bias)], dim=1)
+    enc_kv = A.linear(u, cm.encoder_adapter.weight, cm.encoder_adapter.bias, tc=True)         # [B,N,256]
+    L = torch.cat([A.linear(text, cm.language_adapter.weight, cm.language_adapter.bias, tc=True),
+                   A.linear(time_emb, cm.time_embedding_adapter.weight, cm.time_embedding_adapter.bias, tc=True)], dim=1)
     L = _cross_layer(cm.encoder_cross_attn, L, enc_kv, float(cfg.encoder_dropout), seed, 1)
     for i, layer in enumerate(cm.encoder_self_attn):
         L = _self_layer(layer, L, float(cfg.encoder_dropout), seed, 2 + i)
-    dq = A.linear(enc_kv, cm.decoder_adapter.weight, cm.decoder_adapter.bias)
+    dq = A.linear(enc_kv, cm.decoder_adapter.weight, cm.decoder_adapter.bias, tc=True)
     dq = _cross_layer(cm.decoder_cross_attn, dq, L, float(cfg.decoder_dropout), seed, 8)
-    return A.linear(dq, m.contact_layer.weight, m.contact_layer.bias)
+    return A.linear(dq, m.contact_layer.weight, m.contact_layer.bias, tc=True)

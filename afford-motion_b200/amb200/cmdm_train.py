@@ -116,14 +116,14 @@ def cmdm_forward_train(m, x, timesteps, text_feat, kwargs):
     site = 16
     for layer in m.self_attn_layer.layers:
         sa = layer.self_attn
-        qkv = A.linear(X, sa.in_proj_weight, sa.in_proj_bias)
+        qkv = A.linear(X, sa.in_proj_weight, sa.in_proj_bias, tc=True)
         a = A.AttentionFn.apply(qkv, key_pad, sa.num_heads, float(sa.dropout), seed, site)
-        a = A.linear(a, sa.out_proj.weight, sa.out_proj.bias)
+        a = A.linear(a, sa.out_proj.weight, sa.out_proj.bias, tc=True)
         a = A.DropoutFn.apply(a, layer.dropout1.p, seed, site + 1)
         X = A.LayerNormFn.apply(A.AddFn.apply(X, a, False), layer.norm1.weight, layer.norm1.bias, layer.norm1.eps)
-        f = A.GeluFn.apply(A.linear(X, layer.linear1.weight, layer.linear1.bias))
+        f = A.GeluFn.apply(A.linear(X, layer.linear1.weight, layer.linear1.bias, tc=True))
         f = A.DropoutFn.apply(f, layer.dropout.p, seed, site + 2)
-        f = A.linear(f, layer.linear2.weight, layer.linear2.bias)
+        f = A.linear(f, layer.linear2.weight, layer.linear2.bias, tc=True)
         f = A.DropoutFn.apply(f, layer.dropout2.p, seed, site + 3)
         X = A.LayerNormFn.apply(A.AddFn.apply(X, f, False), layer.norm2.weight, layer.norm2.bias, layer.norm2.eps)
         site += 8

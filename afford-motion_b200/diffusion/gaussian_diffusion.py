@@ -302,32 +302,48 @@ class GaussianDiffusion:
                 ops.add_i32(t_dev, -1)
 
             n = self.num_timesteps
-            it = range(n)
+            graph, unroll = None, 1
+            from amb200 import lib as _lib
+            launches0, per_graph, replays = _lib.launch_count(), 0, 0
+            pbar = None
             if progress:
                 from tqdm.auto import tqdm
-                it = tqdm(it)
-            graph = None
-            from amb200 import lib as _lib
-            launches0, per_step, replays = _lib.launch_count(), 0, 0
-            for k in it:
+                pbar = tqdm(total=n)
+            k = 0
+            while k < n:
                 if step_noise is not None:  # parity harness: injected eps, eager
                     one_step(step_noise(k))
-                elif k == 0 or not use_graph:
+                    done = 1
+                elif k == 0 or not use_graph or not only_final and unroll > 1:
                     one_step()  # eager first step: allocates every workspace before capture
+                    done = 1
                 else:
                     if graph is None:
+                        # one captured graph = `unroll` consecutive denoise steps (fewer host launches per job: the loop is
+                        # host-driven, and a stalled host thread would idle the GPU)
+                        unroll = 8 if (only_final and n - k >= 64) else 1
                         th.cuda.synchronize(device)
                         graph = th.cuda.CUDAGraph()
                         c0 = _lib.launch_count()
                         with th.cuda.graph(graph):
-                            one_step()
-                        per_step = _lib.launch_count() - c0
-                        # capture records without executing: the captured step still has to run for this k
-                    graph.replay()
-                    replays += 1
-                self.last_launches = (_lib.launch_count() - launches0 - per_step * (1 if graph is not None else 0)) + per_step * replays
-                if not only_final or k == n - 1:
-                    yield {"sample": img if k == n - 1 else img.clone(), "pred_xstart": x0 if k == n - 1 else x0.clone()}
+                            for _ in range(unroll):
+                                one_step()
+                        per_graph = _lib.launch_count() - c0
+                        # capture records without executing: the captured steps still have to run
+                    if n - k >= unroll:
+                        graph.replay()
+                        replays += 1
+                        done = unroll
+                    else:
+                        one_step()  # tail shorter than the captured graph
+                        done = 1
+                k += done
+                if pbar is not None:
+                    pbar.update(done)
+                self.last_launches = (_lib.launch_count() - launches0 - (per_graph if graph is not None else 0)) + per_graph * replays
+                if not only_final or k >= n:
+                    last = k >= n
+                    yield {"sample": img if last else img.clone(), "pred_xstart": x0 if last else x0.clone()}
 
     # ------------------------------------------------------------------ training
     def training_losses(self, model, x_start, t, model_kwargs=None, noise=None, **kwargs):

@@ -51,7 +51,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "500",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -238,11 +238,12 @@ def main():
         model._cond_cache = (None, None)  # every job re-encodes its conditioning (new batch semantics)
         job_resident(kw_res)
 
-    for _ in range(args.warmup):
-        resident_once()
     clocks = ClockSampler(local)
     if rank == 0:
-        clocks.start()
+        clocks.start()  # started BEFORE the warm-up: NVML initialisation of the first nvidia-smi poll stalls the driver briefly
+    for _ in range(args.warmup):
+        resident_once()
+    clocks.rows.clear()  # keep only samples taken during the timed regions
     l0 = lib.launch_count()
     ms = timed(resident_once, args.steps)
     launches = 0

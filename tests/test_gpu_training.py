@@ -223,3 +223,28 @@ def test_cdm_training_step_matches_reference_and_oracle(golden_dir):
     for n in names:
         a, b = grads[n].detach().cpu().double(), ograds[n].double()
         assert ((a - b).norm() / (b.norm() + 1e-6 * gscale)).item() < 2e-2, n
+
+
+@pytest.mark.parametrize("M,K,N", [(2048, 32, 32), (2048, 64, 32), (4100, 96, 160), (2500, 512, 1024), (2048, 36, 44)])
+def test_linear_fn_tensor_core_path_vs_fp64(M, K, N):
+    """LinearFn's tcgen05 forward / dX / dW (3-term bf16 split) against fp64."""
+    from amb200 import autograd_ops as A
+    g = torch.Generator().manual_seed(M + K + N)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    up = torch.randn(M, N, generator=g)
+    xd, wd, bd = (t.double().requires_grad_(True) for t in (x, w, b))
+    yd = xd @ wd.T + bd
+    (yd * up.double()).sum().backward()
+    x1, w1, b1 = (t.to(DEV).requires_grad_(True) for t in (x, w, b))
+    assert A._use_tc(M, N, K)
+    y1 = A.linear(x1, w1, b1, tc=True)
+    (y1 * up.to(DEV)).sum().backward()
+
+    def rel(a, ref):
+        return float((a.detach().cpu().double() - ref).norm() / ref.norm())
+    assert rel(y1, yd.detach()) < 2e-5
+    assert rel(x1.grad, xd.grad) < 2e-5
+    assert rel(w1.grad, wd.grad) < 2e-5
+    assert rel(b1.grad, bd.grad) < 2e-5
