@@ -17,12 +17,13 @@ class AttrDict(dict):
         self[k] = v
 
 
-def cdm_model_cfg(num_points: int = 8192, input_feats: int = 6) -> AttrDict:
-    """configs/model/cdm.yaml with the H3D overrides of scripts/t2m_contact/*.sh (arch=Perceiver, no scene model)."""
+def cdm_model_cfg(num_points: int = 8192, input_feats: int = 6, use_scene_model: bool = False, use_color: bool = False) -> AttrDict:
+    """configs/model/cdm.yaml with the H3D overrides of scripts/t2m_contact/*.sh (arch=Perceiver, no scene model);
+    use_scene_model=True gives the HUMANISE / novel variant with the frozen PointTransformerSeg (cdm.yaml:17-25)."""
     return AttrDict(copy.deepcopy(dict(
         name="CDM", input_feats=input_feats, data_repr="contact_cont_joints", time_emb_dim=128,
         text_model=dict(version="ViT-B/32", max_length=32),
-        scene_model=dict(name="PointTransformerSeg", use_scene_model=False, use_color=False, use_openscene=False,
+        scene_model=dict(name="PointTransformerSeg", use_scene_model=use_scene_model, use_color=use_color, use_openscene=False,
                          num_points=num_points, point_feat_dim=32, pretrained_weight=None, freeze=True),
         arch="Perceiver",
         arch_perceiver=dict(last_dim=256, point_pos_emb=True, encoder_q_input_channels=512, encoder_kv_input_channels=256,

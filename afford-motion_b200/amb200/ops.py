@@ -153,6 +153,21 @@ def transition_down_fwd(p, x, new_p, idx, W, shift, out, m, cin, cout, k):
     return out
 
 
+def interpolation(feat, idx, dist2, base, out, n, c, k=3):
+    """pointops.interpolation (pointops.py:164-178) after knnquery: out = base + sum_i w_i feat[idx_i] (base may alias out)."""
+    _chk_cuda(feat, idx, dist2, out)
+    _l.check(_l.load().am_interpolation(_ptr(_f32c(feat)), _ptr(idx), _ptr(dist2), _ptr(base), _ptr(out), n, c, k, _stream()),
+             "am_interpolation")
+    return out
+
+
+def segment_mean(x, offset, out, b, c):
+    """Per-segment row mean of packed features (TransitionUp head form, pointtransformer.py:86-92)."""
+    _chk_cuda(x, offset, out)
+    _l.check(_l.load().am_segment_mean(_ptr(_f32c(x)), _ptr(offset), _ptr(out), b, c, _stream()), "am_segment_mean")
+    return out
+
+
 def cdm_encoder_partial(x_t, xyz, w_ea, b_ea, ln_g, ln_b, qf, ldq, part, B, N, cx, nchunk):
     _l.check(_l.load().am_cdm_encoder_partial(_ptr(x_t), _ptr(xyz), _ptr(w_ea), _ptr(b_ea), _ptr(ln_g), _ptr(ln_b), _ptr(qf), ldq,
                                              _ptr(part), B, N, cx, nchunk, _stream()), "am_cdm_encoder_partial")
@@ -254,6 +269,6 @@ def _wrap(name, fn):
 
 
 for _n in ("randn_", "p_sample_update", "ddim_update", "q_sample", "masked_mse", "add_i32", "linear", "layernorm", "mha_fwd",
-           "gather_time_token", "gather_rows", "furthestsampling", "knnquery", "pt_layer_fwd", "transition_down_fwd",
+           "gather_time_token", "gather_rows", "furthestsampling", "knnquery", "pt_layer_fwd", "transition_down_fwd", "interpolation", "segment_mean",
            "cdm_encoder_partial", "cdm_encoder_combine", "cdm_decoder_point", "linear_skinny", "split_bf16", "linear_tc", "mha_tc_fwd"):
     globals()[_n] = _wrap(_n, globals()[_n])

@@ -62,3 +62,17 @@ def params_version(module: torch.nn.Module) -> int:
     for b in module.buffers():
         v += b._version
     return v
+
+
+def pack_transition_up(tu) -> Dict[str, torch.Tensor]:
+    """pointtransformer.py:72-99 with eval-mode BN folded.  Head form: linear1 over cat(x, g) is used as two column blocks of
+    the same [c, 2c] matrix (w1a = first c columns, w1b = last c); fusion form: linear1+BN (w1, b1) on the fine level,
+    linear2+BN (w2, b2) on the coarse one."""
+    s1, t1 = bn_fold(tu.linear1[1])
+    W1 = c(tu.linear1[0].weight.detach() * s1[:, None])
+    b1 = c(tu.linear1[0].bias.detach() * s1 + t1)
+    if tu.is_head:
+        cc = W1.shape[0]
+        return {"w1": W1, "w1a": W1, "w1b": c(W1[:, cc:]), "b1": b1, "w2": c(tu.linear2[0].weight), "b2": c(tu.linear2[0].bias)}
+    s2, t2 = bn_fold(tu.linear2[1])
+    return {"w1": W1, "b1": b1, "w2": c(tu.linear2[0].weight.detach() * s2[:, None]), "b2": c(tu.linear2[0].bias.detach() * s2 + t2)}

@@ -70,3 +70,88 @@ class SceneEncoderEngine:
             for bw in w["blocks"]:
                 x = self._block(bw, p, x, o, B * n_seg, cout, NSAMPLE[s])
         return x.view(B, n_seg, x.shape[1])
+
+
+class SceneSegEngine(SceneEncoderEngine):
+    """GPU execution of the frozen PointTransformerSeg scene model (pointtransformer.py:126-201) in
+    eval mode: five TransitionDown/Block encoder stages (planes 32..512, blocks [2,3,4,6,3]) and five TransitionUp/Block
+    decoder stages -> per-point features [B, N, 32].  Runs once per batch (the reference re-runs it on every denoise step,
+    cdm.py:508); reuses the encoder kernels plus am_segment_mean / am_interpolation for TransitionUp (:82-99)."""
+
+    def pack(self):
+        from .pack import pack_transition_up
+        m = self.m
+        enc, dec = [], []
+        for s in range(5):
+            stage = getattr(m, f"enc{s + 1}")
+            enc.append({"td": pack_transition_down(stage[0]), "blocks": [pack_pt_block(b) for b in list(stage)[1:]]})
+            dstage = getattr(m, f"dec{s + 1}")
+            dec.append({"tu": pack_transition_up(dstage[0]), "blocks": [pack_pt_block(b) for b in list(dstage)[1:]]})
+        self.w = {"enc": enc, "dec": dec}
+
+    @torch.no_grad()
+    def forward(self, xyz: torch.Tensor, feat: torch.Tensor) -> torch.Tensor:
+        """xyz [B,N,3], feat [B,N,c-3] (ignored when c == 3) -> [B, N, 32]"""
+        if self.w is None:
+            self.pack()
+        B, N, _ = xyz.shape
+        assert N % 256 == 0, "PointTransformerSeg needs num_points divisible by 4^4 (four stride-4 stages)"
+        dev = xyz.device
+        strides, ns = [1, 4, 4, 4, 4], [8, 16, 16, 16, 16]
+        p = xyz.reshape(B * N, 3).float().contiguous()
+        x = p if self.m.c == 3 else torch.cat((p, feat.reshape(B * N, -1).float()), 1).contiguous()
+        n_seg = N
+        o = (torch.arange(1, B + 1, device=dev, dtype=torch.int32) * n_seg).contiguous()
+        lv = []
+        for s in range(5):
+            w = self.w["enc"][s]
+            cin, cout = x.shape[1], w["td"]["W"].shape[0]
+            if strides[s] == 1:
+                y = torch.empty(B * n_seg, cout, device=dev)
+                ops.linear(x, w["td"]["W"], y, B * n_seg, cout, cin, bias=w["td"]["shift"], act="relu")
+                x = y
+            else:
+                m_seg = n_seg // strides[s]
+                n_o = (torch.arange(1, B + 1, device=dev, dtype=torch.int32) * m_seg).contiguous()
+                m = B * m_seg
+                fidx = ops.furthestsampling(p, o, n_o, n_max=n_seg, m_total=m)
+                n_p = torch.empty(m, 3, device=dev)
+                ops.gather_rows(p, fidx, n_p, m, 3)
+                kidx, _ = ops.knnquery(ns[s], p, n_p, o, n_o)
+                y = torch.empty(m, cout, device=dev)
+                ops.transition_down_fwd(p, x, n_p, kidx, w["td"]["W"], w["td"]["shift"], y, m, cin, cout, ns[s])
+                p, x, o, n_seg = n_p, y, n_o, m_seg
+            for bw in w["blocks"]:
+                x = self._block(bw, p, x, o, B * n_seg, cout, ns[s])
+            lv.append([p, x, o, n_seg])
+        for s in range(4, -1, -1):
+            w = self.w["dec"][s]
+            tu = w["tu"]
+            p1, x1, o1, n1 = lv[s]
+            n, c = B * n1, tu["w1"].shape[0]
+            y = torch.empty(n, c, device=dev)
+            if s == 4:
+                # head form: linear1(cat(x, g_seg)) = W1a x + (W1b g_seg + b1), g_seg = relu(W2 mean_seg(x) + b2) — the
+                # second summand is one row per segment, added through the GEMM's broadcast-residual path (row // n1)
+                mean = torch.empty(B, c, device=dev)
+                ops.segment_mean(x1, o1, mean, B, c)
+                g = torch.empty(B, c, device=dev)
+                ops.linear(mean, tu["w2"], g, B, c, c, bias=tu["b2"], act="relu")
+                gb = torch.empty(B, c, device=dev)
+                ops.linear(g, tu["w1b"], gb, B, c, c, bias=tu["b1"])
+                rows = torch.empty(n, c, device=dev)
+                seg_of_row = torch.arange(n, device=dev, dtype=torch.int32) // n1
+                ops.gather_rows(gb, seg_of_row.contiguous(), rows, n, c)
+                ops.linear(x1, tu["w1a"], y, n, c, c, residual=rows, act="relu_after_res", ldw=2 * c)
+            else:
+                p2, x2, o2, _ = lv[s + 1]
+                ops.linear(x1, tu["w1"], y, n, c, c, bias=tu["b1"], act="relu")
+                z = torch.empty(x2.shape[0], c, device=dev)
+                ops.linear(x2, tu["w2"], z, x2.shape[0], c, x2.shape[1], bias=tu["b2"], act="relu")
+                kidx, d2 = ops.knnquery(3, p2, p1, o2, o1)
+                ops.interpolation(z, kidx, d2, y, y, n, c, 3)
+            x = y
+            for bw in w["blocks"]:
+                x = self._block(bw, p1, x, o1, n, c, ns[s])
+            lv[s][1] = x
+        return lv[0][1].view(B, N, -1)

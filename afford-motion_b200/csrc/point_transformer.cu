@@ -16,12 +16,15 @@ pt_layer_kernel(const float* __restrict__ p, const float* __restrict__ qkv, cons
                 const float* __restrict__ bp2, const float* __restrict__ bnw_s, const float* __restrict__ bnw_t,
                 const float* __restrict__ ww1, const float* __restrict__ bw1, const float* __restrict__ ww2,
                 const float* __restrict__ bw2, const float* __restrict__ post_s, const float* __restrict__ post_t,
-                float* __restrict__ out, int n, int c, int k) {
+                float* __restrict__ out, int n, int c, int k, int ww1_in_smem) {
     extern __shared__ __align__(16) float sm[];
     const int c8 = c / 8, cs = c + 1, c8s = c8 + 1;
-    float* s_ww1 = sm;                      // [c8][c+1]
-    float* s_ww2 = s_ww1 + c8 * cs;         // [c8][c8+1]
+    const int nwarps = blockDim.x >> 5;
+    float* s_ww1 = sm;                      // [c8][c+1]  (c <= 256; at c = 512 ww1 stays in global / L1, see am_pt_layer_fwd)
+    float* s_ww2 = s_ww1 + (ww1_in_smem ? c8 * cs : 0);  // [c8][c8+1]
     float* s_warp = s_ww2 + c8 * c8s;
+    const float* w1base = ww1_in_smem ? s_ww1 : ww1;
+    const int w1s = ww1_in_smem ? cs : c;
     const int per_warp = k * cs + 2 * k * c8s + k * 4;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* W = s_warp + warp * per_warp;    // [k][c+1]
@@ -29,11 +32,12 @@ pt_layer_kernel(const float* __restrict__ p, const float* __restrict__ qkv, cons
     float* t2 = t1 + k * c8s;               // [k][c8+1]
     float* hs = t2 + k * c8s;               // [k][4] : relu(linear_p.0/1) hidden (3) + neighbour index
 
-    for (int i = threadIdx.x; i < c8 * c; i += blockDim.x) s_ww1[(i / c) * cs + (i % c)] = ww1[i];
+    if (ww1_in_smem)
+        for (int i = threadIdx.x; i < c8 * c; i += blockDim.x) s_ww1[(i / c) * cs + (i % c)] = ww1[i];
     for (int i = threadIdx.x; i < c8 * c8; i += blockDim.x) s_ww2[(i / c8) * c8s + (i % c8)] = ww2[i];
     __syncthreads();
 
-    const int pt = blockIdx.x * PT_WARPS + warp;
+    const int pt = blockIdx.x * nwarps + warp;
     if (pt >= n) return;
     const int ld = 3 * c;
     const float px = p[3 * (int64_t)pt], py = p[3 * (int64_t)pt + 1], pz = p[3 * (int64_t)pt + 2];
@@ -64,7 +68,7 @@ pt_layer_kernel(const float* __restrict__ p, const float* __restrict__ qkv, cons
     for (int e = lane; e < k * c8; e += 32) {
         int j = e / c8, o = e % c8;
         float acc = bw1[o];
-        const float* wr = s_ww1 + o * cs;
+        const float* wr = w1base + o * w1s;
         const float* xr = W + j * cs;
         for (int ch = 0; ch < c; ++ch) acc = fmaf(wr[ch], xr[ch], acc);
         t1[j * c8s + o] = fmaxf(acc, 0.f);
@@ -165,6 +169,41 @@ transition_down_kernel(const float* __restrict__ p, const float* __restrict__ x,
     }
 }
 
+// ---------------------------------------------------------------- 3-NN inverse-distance interpolation (TransitionUp)
+__global__ void interpolation_kernel(const float* __restrict__ feat, const int32_t* __restrict__ idx, const float* __restrict__ dist2,
+                                     const float* base, float* out, int n, int c, int k) {
+    const int64_t total = (int64_t)n * c;
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(g / c), ch = (int)(g - (int64_t)j * c);
+        float norm = 0.f;
+        for (int i = 0; i < k; ++i) norm += 1.0f / (sqrtf(dist2[(int64_t)j * k + i]) + 1e-8f);
+        float acc = 0.f;
+        for (int i = 0; i < k; ++i) {
+            float w = (1.0f / (sqrtf(dist2[(int64_t)j * k + i]) + 1e-8f)) / norm;
+            acc += feat[(int64_t)idx[(int64_t)j * k + i] * c + ch] * w;
+        }
+        out[g] = (base ? base[g] : 0.f) + acc;
+    }
+}
+
+// ---------------------------------------------------------------- per-segment mean (TransitionUp head form)
+__global__ void segment_mean_kernel(const float* __restrict__ x, const int32_t* __restrict__ offset, float* __restrict__ out, int c) {
+    const int s = blockIdx.x;
+    const int start = s == 0 ? 0 : offset[s - 1], end = offset[s];
+    const int ch = blockIdx.y * 32 + (threadIdx.x & 31), row0 = threadIdx.x >> 5, nrow = blockDim.x >> 5;
+    __shared__ float part[8][33];
+    float acc = 0.f;
+    if (ch < c)
+        for (int j = start + row0; j < end; j += nrow) acc += x[(int64_t)j * c + ch];
+    part[row0][threadIdx.x & 31] = acc;
+    __syncthreads();
+    if (row0 == 0 && ch < c) {
+        float t = 0.f;
+        for (int r = 0; r < nrow; ++r) t += part[r][threadIdx.x];
+        out[(int64_t)s * c + ch] = end > start ? t / (float)(end - start) : 0.f;
+    }
+}
+
 }  // namespace
 
 extern "C" int am_pt_layer_fwd(const float* p, const float* qkv, const int32_t* idx, const float* wp1, const float* bp1, const float* wp2,
@@ -176,7 +215,16 @@ extern "C" int am_pt_layer_fwd(const float* p, const float* qkv, const int32_t* 
     AM_REQUIRE(n > 0 && c >= 8 && c % 8 == 0 && c <= 512 && k >= 1 && k <= 32, AM_EINVAL, "am_pt_layer_fwd: bad dims");
     AM_REQUIRE((post_s == nullptr) == (post_t == nullptr), AM_EINVAL, "am_pt_layer_fwd: post_s/post_t must come together");
     int c8 = c / 8;
-    size_t smem = sizeof(float) * ((size_t)c8 * (c + 1) + (size_t)c8 * (c8 + 1) + (size_t)PT_WARPS * (k * (c + 1) + 2 * k * (c8 + 1) + k * 4));
+    // c <= 256: 8 warps per CTA with ww1 staged in shared memory.  c = 512 (enc5 / dec5 of PointTransformerSeg, n = B*32 points):
+    // ww1 (128 KB) is read through L1 instead and the CTA shrinks until the per-warp neighbour tiles fit.
+    int nw = PT_WARPS, w1smem = 1;
+    auto need = [&](int warps, int in_smem) {
+        return sizeof(float) * ((size_t)(in_smem ? c8 * (c + 1) : 0) + (size_t)c8 * (c8 + 1) +
+                                (size_t)warps * (k * (c + 1) + 2 * k * (c8 + 1) + k * 4));
+    };
+    size_t smem = need(nw, w1smem);
+    if (smem > 227 * 1024) { w1smem = 0; smem = need(nw, 0); }
+    while (smem > 227 * 1024 && nw > 1) { nw >>= 1; smem = need(nw, 0); }
     AM_REQUIRE(smem <= 227 * 1024, AM_EINVAL, "am_pt_layer_fwd: c*k too large for shared memory");
     static size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {
@@ -186,8 +234,8 @@ extern "C" int am_pt_layer_fwd(const float* p, const float* qkv, const int32_t* 
         }
         attr = 227 * 1024;
     }
-    pt_layer_kernel<<<cdiv(n, PT_WARPS), PT_WARPS * 32, smem, as_stream(stream)>>>(p, qkv, idx, wp1, bp1, wp2, bp2, bnw_s, bnw_t, ww1, bw1,
-                                                                                    ww2, bw2, post_s, post_t, out, n, c, k);
+    pt_layer_kernel<<<cdiv(n, nw), nw * 32, smem, as_stream(stream)>>>(p, qkv, idx, wp1, bp1, wp2, bp2, bnw_s, bnw_t, ww1, bw1, ww2, bw2,
+                                                                        post_s, post_t, out, n, c, k, w1smem);
     AM_LAUNCH_CHECK("pt_layer_fwd");
     return AM_OK;
 }
@@ -210,5 +258,22 @@ extern "C" int am_transition_down_fwd(const float* p, const float* x, const floa
     }
     transition_down_kernel<<<cdiv(m, TD_PTS), 256, smem, as_stream(stream)>>>(p, x, new_p, idx, W, shift, out, m, cin, cout);
     AM_LAUNCH_CHECK("transition_down_fwd");
+    return AM_OK;
+}
+
+extern "C" int am_interpolation(const float* feat, const int32_t* idx, const float* dist2, const float* base, float* out, int n, int c,
+                                int k, am_stream_t stream) {
+    AM_REQUIRE(feat && idx && dist2 && out && n > 0 && c > 0 && k >= 1 && k <= 16, AM_EINVAL, "am_interpolation: bad args");
+    int64_t blocks = ((int64_t)n * c + 255) / 256;
+    int grid = (int)(blocks < (int64_t)AM_NUM_SMS * 8 ? blocks : (int64_t)AM_NUM_SMS * 8);
+    interpolation_kernel<<<grid, 256, 0, as_stream(stream)>>>(feat, idx, dist2, base, out, n, c, k);
+    AM_LAUNCH_CHECK("interpolation");
+    return AM_OK;
+}
+
+extern "C" int am_segment_mean(const float* x, const int32_t* offset, float* out, int b, int c, am_stream_t stream) {
+    AM_REQUIRE(x && offset && out && b > 0 && c > 0, AM_EINVAL, "am_segment_mean: bad args");
+    segment_mean_kernel<<<dim3(b, cdiv(c, 32)), 256, 0, as_stream(stream)>>>(x, offset, out, c);
+    AM_LAUNCH_CHECK("segment_mean");
     return AM_OK;
 }

@@ -323,12 +323,15 @@ class GaussianDiffusion:
                         # host-driven, and a stalled host thread would idle the GPU)
                         unroll = 8 if (only_final and n - k >= 64) else 1
                         th.cuda.synchronize(device)
+                        import time as _time
+                        _t0 = _time.perf_counter()
                         graph = th.cuda.CUDAGraph()
                         c0 = _lib.launch_count()
                         with th.cuda.graph(graph):
                             for _ in range(unroll):
                                 one_step()
                         per_graph = _lib.launch_count() - c0
+                        self.last_capture_ms = 1e3 * (_time.perf_counter() - _t0)  # host cost of capture + instantiate (per job)
                         # capture records without executing: the captured steps still have to run
                     if n - k >= unroll:
                         graph.replay()

@@ -2,14 +2,15 @@
 
 Same class name / registry entry, constructor, `forward(x, timesteps, **kwargs)`, config keys
 (configs/model/cdm.yaml) and state_dict names; arithmetic in amb200.cdm_engine (CUDA).
-Out of scope: the ablation archs ContactMLP / ContactPointTrans(V2) and the frozen
-PointTransformerSeg scene model (§8 f3, "next") — selecting them raises NotImplementedError.
+The frozen PointTransformerSeg scene model of the HUMANISE / novel configs (cdm.py:436-446,508) runs once per
+batch in amb200.scene_engine.SceneSegEngine.  Out of scope: the ablation archs ContactMLP /
+ContactPointTrans(V2) — selecting them raises NotImplementedError.
 """
 import torch
 import torch.nn as nn
 
 from models.base import Model
-from models.functions import encode_text_clip, get_lang_feat_dim_type, load_and_freeze_clip_model
+from models.functions import encode_text_clip, get_lang_feat_dim_type, load_and_freeze_clip_model, load_scene_model
 from models.modules import CrossAttentionLayer, SelfAttentionBlock, TimestepEmbedder
 
 
@@ -52,9 +53,14 @@ class CDM(nn.Module):
             self.point_feat_dim = 0
         elif cfg.scene_model.use_openscene:
             self.point_feat_dim = cfg.scene_model.point_feat_dim  # features arrive precomputed in c_pc_feat
-        else:
-            raise NotImplementedError("frozen PointTransformerSeg scene model is a 'next' row (SURVEY §8 f3); "
-                                      "use scene_model.use_scene_model=False (H3D config) or precomputed point features")
+        else:  # frozen PointTransformerSeg (cdm.py:436-446): per-point features computed ONCE per batch by SceneSegEngine
+            if not cfg.scene_model.freeze:
+                raise NotImplementedError("a trainable scene model is not used by any reference config (cdm.yaml:25 freeze: true)")
+            self.scene_model_dim = 3 + int(cfg.scene_model.use_color) * 3
+            self.freeze_scene_model = cfg.scene_model.freeze
+            self.scene_model = load_scene_model(cfg.scene_model.name, self.scene_model_dim, cfg.scene_model.num_points,
+                                                cfg.scene_model.pretrained_weight, freeze=self.freeze_scene_model)
+            self.point_feat_dim = cfg.scene_model.point_feat_dim
         self.arch = cfg.arch
         if self.arch != "Perceiver":
             raise NotImplementedError("afford-motion_b200 implements CDM arch='Perceiver' (the arch every reference script selects)")
@@ -77,19 +83,42 @@ class CDM(nn.Module):
     def encode_condition(self, **kwargs):
         self.engine.refresh()
         xyz = kwargs["c_pc_xyz"]
-        pf = kwargs.get("c_pc_feat") if self.point_feat_dim > 0 else None
+        has_scene = hasattr(self, "scene_model")
+        pf = kwargs.get("c_pc_feat") if (self.point_feat_dim > 0 or has_scene) else None
 
         def tk(t):
             return None if t is None else (t.data_ptr(), t._version, tuple(t.shape))
-        key = (tuple(kwargs["c_text"]), tk(xyz), tk(pf), self.engine._version)
+        key = (tuple(kwargs["c_text"]), tk(xyz), tk(pf), self.engine._version, self._scene_version())
         if self._cond_cache[0] == key:
             return self._cond_cache[1]
         text = encode_text_clip(self.text_model, kwargs["c_text"], max_length=self.text_max_length, device=xyz.device).detach().float()
-        if pf is not None and self.point_feat_dim == 1 and pf.shape[-1] != 1:  # cdm.py:500-504 (openscene similarity feature)
+        if has_scene:  # cdm.py:508: scene_model((xyz, feat)).detach() — hoisted out of the denoise loop
+            pf = self.scene_point_features(xyz, pf)
+        elif pf is not None and self.point_feat_dim == 1 and pf.shape[-1] != 1:  # cdm.py:500-504 (openscene similarity feature)
             pf = torch.einsum("bnd,bmd->bnm", pf, text.unsqueeze(1))
         cond = self.engine.encode_condition(text, xyz, pf)
         self._cond_cache = (key, cond)
         return cond
+
+    def _scene_version(self):
+        if not hasattr(self, "scene_model"):
+            return 0
+        from amb200.pack import params_version
+        return params_version(self.scene_model)
+
+    @torch.no_grad()
+    def scene_point_features(self, xyz, feat):
+        """Frozen PointTransformerSeg features [B,N,32] (eval-mode BatchNorm always: utils/training.py:111-116)."""
+        eng = self.scene_model.engine
+        v = self._scene_version()
+        if getattr(eng, "_packed_version", None) != v:
+            eng.pack()
+            eng._packed_version = v
+        if self.scene_model_dim == 3:
+            feat = None
+        elif feat is None:
+            raise ValueError("scene_model.use_color=True needs c_pc_feat [B,N,3]")
+        return eng.forward(xyz.float(), None if feat is None else feat.float())
 
     def forward(self, x, timesteps, **kwargs):
         """x [bs, num_points, contact_dim], timesteps int64 [bs] -> [bs, num_points, contact_dim]  (cdm.py:474-513)."""
@@ -98,6 +127,8 @@ class CDM(nn.Module):
         if self.training:  # autograd graph of libamb200 kernels, unfolded Perceiver, attention dropout (cdm.yaml:41,48)
             from amb200.cdm_train import cdm_forward_train
             text = encode_text_clip(self.text_model, kwargs["c_text"], max_length=self.text_max_length, device=x.device).detach().float()
+            if hasattr(self, "scene_model"):
+                kwargs = dict(kwargs, c_pc_feat=self.scene_point_features(kwargs["c_pc_xyz"], kwargs.get("c_pc_feat")))
             return cdm_forward_train(self, x.float().contiguous(), timesteps, text, kwargs)
         cond = self.encode_condition(**kwargs)
         t_dev = timesteps.to(device=x.device, dtype=torch.int32).contiguous()

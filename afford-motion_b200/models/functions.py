@@ -71,3 +71,19 @@ def get_lang_feat_dim_type(model_name: str):
     if model_name == "ViT-L/14@336px":
         return 768, "clip"
     raise NotImplementedError(model_name)
+
+
+def load_scene_model(model_name: str, model_dim: int, num_points: int, pretrained_weight: str = None, freeze: bool = True) -> torch.nn.Module:
+    """functions.py:96-126.  PointTransformerSeg is the scene model every CDM config names (configs/model/cdm.yaml:18);
+    PointTransformerEnc is only used by the ContactPointTrans ablations, which are out of scope."""
+    from models.scene_models.pointtransformer import pointtransformer_seg_repro
+    if model_name != "PointTransformerSeg":
+        raise NotImplementedError(model_name)
+    scene_model = pointtransformer_seg_repro(c=model_dim, num_points=num_points)
+    if pretrained_weight is not None:
+        scene_model.load_pretrained_weight(weight_path=pretrained_weight)
+    if freeze:
+        scene_model.eval()
+        for p in scene_model.parameters():
+            p.requires_grad = False
+    return scene_model

@@ -47,11 +47,14 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index=0):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.rows, self.proc, self.gpu, self.phase = [], None, gpu_index, None
+
+    def mark(self, phase):
+        self.phase = phase
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "500",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -59,24 +62,29 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([c.strip() for c in line.split(",")] + [self.phase])
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
         self.proc.terminate()
-        sm, smax, reasons = [], None, set()
+        sm, smax, reasons, by_phase, pw = [], None, set(), {}, []
         for r in self.rows:
             try:
-                sm.append(float(r[1])); smax = float(r[2])
+                sm.append(float(r[1])); smax = float(r[2]); pw.append(float(r[3]))
             except Exception:
                 continue
+            if r[-1]:
+                by_phase.setdefault(r[-1], []).append(float(r[1]))
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+        med = lambda v: sorted(v)[len(v) // 2] if v else None
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm),
+                "sm_mhz_min": sm[0] if sm else None, "power_w_max": max(pw) if pw else None,
+                "sm_mhz_by_phase": {k: {"median": med(v), "min": min(v), "n": len(v)} for k, v in by_phase.items()}}
 
 
 def synth_host_inputs(rank):
@@ -221,15 +229,20 @@ def main():
         amdist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, k):
+    job_ms = {}
+
+    def timed(fn, k, tag):
         barrier()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        for _ in range(k):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(k + 1)]
+        clocks.mark(tag)
+        ev[0].record()
+        for i in range(k):
             fn()
-        e.record()
+            ev[i + 1].record()
         barrier()
-        return amdist.max_over_ranks(s.elapsed_time(e), device=dev)  # the job is as slow as its slowest rank
+        clocks.mark(None)
+        job_ms[tag] = [round(ev[i].elapsed_time(ev[i + 1]), 2) for i in range(k)]
+        return amdist.max_over_ranks(ev[0].elapsed_time(ev[k]), device=dev)  # the job is as slow as its slowest rank
 
     text_dev["t"] = host["text"].to(dev)
     kw_res = dict(c_text=host["texts"], c_pc_xyz=host["xyz"].to(dev), c_pc_contact=host["contact"].to(dev), x_mask=host["x_mask"].to(dev))
@@ -245,12 +258,12 @@ def main():
         resident_once()
     clocks.rows.clear()  # keep only samples taken during the timed regions
     l0 = lib.launch_count()
-    ms = timed(resident_once, args.steps)
+    ms = timed(resident_once, args.steps, "resident")
     launches = 0
     # launches: per job = eager + graph replays (recorded by the loop) + conditioning encode (counted directly)
     resident_once()
     launches_per_job = diff.last_launches
-    ms_e2e = timed(job_e2e, args.steps)
+    ms_e2e = timed(job_e2e, args.steps, "e2e")
     clk = clocks.stop() if rank == 0 else None
     del l0, launches
 
@@ -310,7 +323,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "denoise-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches_per_job * args.steps), "clocks": clk, "roofline": roof, "cpu_baseline": cpu_base,
-                "kernels": prof_out}
+                "kernels": prof_out, "job_ms": job_ms, "graph_capture_ms_per_job": getattr(diff, "last_capture_ms", None)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -144,6 +144,17 @@ int am_pt_layer_fwd(const float* p, const float* qkv, const int32_t* idx, const 
 int am_transition_down_fwd(const float* p, const float* x, const float* new_p, const int32_t* idx, const float* W,
                            const float* shift, float* out, int m, int cin, int cout, int k, am_stream_t stream);
 
+/* pointops.interpolation (models/scene_models/pointops.py:164-178) after a k=3 kNN of new_xyz in xyz:
+ *   d_i = sqrt(dist2[j,i]);  r_i = 1/(d_i + 1e-8);  w_i = r_i / sum r;
+ *   out[j,:] = (base ? base[j,:] : 0) + sum_i w_i * feat[idx[j,i], :]
+ * `base` is the other summand of TransitionUp.forward's fusion form (pointtransformer.py:97) and may alias `out`. */
+int am_interpolation(const float* feat, const int32_t* idx, const float* dist2, const float* base, float* out, int n,
+                     int c, int k, am_stream_t stream);
+
+/* Per-segment mean of packed rows (TransitionUp head form, pointtransformer.py:86-92: x_b.sum(0, True) / cnt):
+ *   out[s,:] = sum_{j in [offset[s-1], offset[s])} x[j,:] / (offset[s] - offset[s-1]);  offset = cumulative ends. */
+int am_segment_mean(const float* x, const int32_t* offset, float* out, int b, int c, am_stream_t stream);
+
 /* ------------------------------------------------------------------ CDM Perceiver (models/cdm.py:155-188)
  * Encoder cross-attention over N points with the exact algebraic fold of SURVEY §7.2:
  *   u = cat(x_t, xyz) [N,cin];  kvn = LN_kv(W_ea u + b_ea) [256]

@@ -73,3 +73,48 @@ def scene_map_encoder(sd, pre, xyz, feat, blocks=(2, 2, 2, 2)):
         for bi in range(1, blocks[s]):
             x = pt_block(sd, f"{e}.{bi}", p, x, o, ns[s])
     return x.view(B, -1, x.shape[-1])
+
+
+def transition_up(sd, pre, pxo1, pxo2=None):
+    """pointtransformer.py:82-99.  Head form (pxo2 None): per-segment mean -> linear2+ReLU, repeated and concatenated to
+    every row -> linear1+BN+ReLU.  Fusion form: linear1+BN+ReLU(x1) + 3-NN interpolation of linear2+BN+ReLU(x2)."""
+    if pxo2 is None:
+        _, x, o = pxo1
+        rows, s = [], 0
+        for e in o.tolist():
+            xb = x[s:e]
+            g = F.relu(lin(sd, pre + ".linear2.0", xb.sum(0, True) / (e - s)))
+            rows.append(torch.cat((xb, g.repeat(e - s, 1)), 1))
+            s = e
+        h = lin(sd, pre + ".linear1.0", torch.cat(rows, 0))
+        return F.relu(bn_eval(sd, pre + ".linear1.1", h))
+    p1, x1, o1 = pxo1
+    p2, x2, o2 = pxo2
+    a = F.relu(bn_eval(sd, pre + ".linear1.1", lin(sd, pre + ".linear1.0", x1)))
+    b = F.relu(bn_eval(sd, pre + ".linear2.1", lin(sd, pre + ".linear2.0", x2)))
+    return a + P.interpolation(p2, p1, b, o2, o1)
+
+
+def point_transformer_seg(sd, pre, xyz, feat, blocks=(2, 3, 4, 6, 3), c=6):
+    """PointTransformerSeg.forward, (p, x) input form (pointtransformer.py:166-201) -> [B, N, 32].
+    `pre` is the state_dict prefix of the scene model ('' or 'scene_model')."""
+    B, N, _ = xyz.shape
+    dot = (pre + ".") if pre else ""
+    p = xyz.reshape(B * N, 3).contiguous()
+    x = p if c == 3 else torch.cat((p, feat.reshape(B * N, -1)), 1)
+    o = torch.tensor([N * (i + 1) for i in range(B)], dtype=torch.int32)
+    strides, ns = [1, 4, 4, 4, 4], [8, 16, 16, 16, 16]
+    lv = []
+    for s in range(5):
+        e = f"{dot}enc{s + 1}"
+        p, x, o = transition_down(sd, e + ".0", p, x, o, strides[s], ns[s])
+        for bi in range(1, blocks[s]):
+            x = pt_block(sd, f"{e}.{bi}", p, x, o, ns[s])
+        lv.append([p, x, o])
+    for s in range(4, -1, -1):
+        d = f"{dot}dec{s + 1}"
+        p, x, o = lv[s]
+        x = transition_up(sd, d + ".0", lv[s]) if s == 4 else transition_up(sd, d + ".0", lv[s], lv[s + 1])
+        x = pt_block(sd, d + ".1", p, x, o, ns[s])  # _make_dec(blocks=2): one block after the TransitionUp
+        lv[s] = [p, x, o]
+    return lv[0][1].view(B, N, -1)

@@ -73,6 +73,16 @@ def cmdm_cfg(num_points):
     )
 
 
+ONLY = [a for a in sys.argv[1:] if not a.startswith("-")]  # e.g. `make_golden.py scene_seg` rewrites only matching fixtures
+
+
+def _save(name, arrs):
+    if ONLY and not any(o in name for o in ONLY):
+        return
+    np.savez_compressed(os.path.join(HERE, name), **arrs)
+    print("wrote", name)
+
+
 def main():
     install_stubs()
     from amb200 import synth
@@ -124,7 +134,7 @@ def main():
     out["linear1000_betas"] = gd.get_named_beta_schedule("linear", 1000)
     out["space_300_10_15_20"] = np.array(sorted(space_timesteps(300, [10, 15, 20])))
     out["space_1000_ddim50"] = np.array(sorted(space_timesteps(1000, "ddim50")))
-    np.savez_compressed(os.path.join(HERE, "diffusion_tables.npz"), **out)
+    _save("diffusion_tables.npz", out)
 
     # sampler / loss steps with a dummy model that returns a fixed x0_hat
     T = 1000
@@ -167,7 +177,7 @@ def main():
         steps["mse_mixed"] = terms["mse"].numpy()
     finally:
         torch.randn_like = real_randn_like
-    np.savez_compressed(os.path.join(HERE, "diffusion_steps.npz"), **steps)
+    _save("diffusion_steps.npz", steps)
 
     # ---------------------------------------------------------------- CDM (config 1: B=2, N=1024)
     torch.manual_seed(0)
@@ -185,7 +195,7 @@ def main():
             t = torch.tensor(tv)
             res[f"t_{tag}"] = t.numpy()
             res[f"out_{tag}"] = cdm(x, t, c_text=["a"] * B, c_pc_xyz=xyz, c_pc_feat=None).numpy()
-    np.savez_compressed(os.path.join(HERE, "cdm_b2_n1024.npz"), **res)
+    _save("cdm_b2_n1024.npz", res)
 
     # ---------------------------------------------------------------- CMDM (B=3; N=1024 and N=8192)
     for N in (1024, 8192):
@@ -240,7 +250,7 @@ def main():
                 res["chain_t"] = np.array(chain_t)
                 res["chain_out"] = img.numpy()
         res["x_mask"] = x_mask.numpy()
-        np.savez_compressed(os.path.join(HERE, f"cmdm_b3_n{N}.npz"), **res)
+        _save(f"cmdm_b3_n{N}.npz", res)
 
     # ---------------------------------------------------------------- CMDM training step (train mode, dropout p=0), B=2, N=1024
     torch.manual_seed(0)
@@ -285,7 +295,7 @@ def main():
     for k in ("contact_encoder.enc1.0.bn.running_mean", "contact_encoder.enc1.0.bn.running_var",
               "contact_encoder.enc3.1.transformer2.linear_w.3.running_var"):
         tr["buf::" + k] = sdt[k].numpy()
-    np.savez_compressed(os.path.join(HERE, "cmdm_train_b2_n1024.npz"), **tr)
+    _save("cmdm_train_b2_n1024.npz", tr)
 
     # ---------------------------------------------------------------- CDM training step (train mode, dropout p=0), B=2, N=1024
     torch.manual_seed(0)
@@ -314,9 +324,42 @@ def main():
     for k in ("contact_layer.weight", "contact_model.encoder_adapter.weight", "contact_model.decoder_cross_attn.0.module.attention.q_proj.bias",
               "contact_model.encoder_cross_attn.0.module.kv_norm.weight", "timestep_embedder.time_embed.2.bias"):
         tr["grad::" + k] = dict(cdm.named_parameters())[k].grad.numpy()
-    np.savez_compressed(os.path.join(HERE, "cdm_train_b2_n1024.npz"), **tr)
+    _save("cdm_train_b2_n1024.npz", tr)
 
-    with open(os.path.join(HERE, "state_keys.json"), "w") as f:
+    # ---------------------------------------------------------------- frozen PointTransformerSeg scene model (§8 f3) + CDM using it
+    import models.scene_models.pointtransformer as rpt
+    torch.cuda.FloatTensor = lambda *shape: torch.FloatTensor(*shape)  # pointops.py:175
+    B, N = 2, 1024
+    xyz = synth.scene_points(B, N, seed=51, dup_frac=0.05)
+    color = torch.rand(B, N, 3, generator=torch.Generator().manual_seed(51))
+    seg_res = {}
+    for cdim in (3, 6):
+        torch.manual_seed(0)
+        seg = rpt.pointtransformer_seg_repro(c=cdim, num_points=N).eval()
+        shapes = {k: tuple(v.shape) for k, v in seg.state_dict().items()}
+        keys[f"PointTransformerSeg_c{cdim}"] = {k: list(v) for k, v in shapes.items()}
+        seg.load_state_dict(synth.fill_state_dict(shapes, seed=0), strict=False)
+        with torch.no_grad():
+            seg_res[f"feat_c{cdim}"] = seg((xyz, color)).numpy()
+    cfg_s = json.loads(json.dumps(CDM_CFG))
+    cfg_s["scene_model"].update(use_scene_model=True, use_color=False, num_points=N)
+    torch.manual_seed(0)
+    cdm_s = rcdm.CDM(DictConfig(cfg_s), device="cpu").eval()
+    shapes = {k: tuple(v.shape) for k, v in cdm_s.state_dict().items()}
+    keys["CDM_scene"] = {k: list(v) for k, v in shapes.items()}
+    cdm_s.load_state_dict(synth.fill_state_dict(shapes, seed=0), strict=False)
+    text_holder["feat"] = synth.text_features(B, seed=51)
+    x = torch.randn(B, N, 6, generator=torch.Generator().manual_seed(52))
+    tt = torch.tensor([450, 2])
+    with torch.no_grad():
+        seg_res["cdm_scene_out"] = cdm_s(x, tt, c_text=["a"] * B, c_pc_xyz=xyz, c_pc_feat=color).numpy()
+    seg_res["t"] = tt.numpy()
+    _save("scene_seg_b2_n1024.npz", seg_res)
+
+    kp = os.path.join(HERE, "state_keys.json")
+    if ONLY and os.path.exists(kp):
+        keys = {**json.load(open(kp)), **keys}
+    with open(kp, "w") as f:
         json.dump(keys, f, indent=0, sort_keys=True)
     print("golden fixtures written to", HERE)
 

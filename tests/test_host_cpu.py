@@ -25,10 +25,12 @@ def test_state_dict_keys_match_reference(golden_dir):
     from models.base import Model
     import models  # noqa: F401
     keys = json.load(open(os.path.join(golden_dir, "state_keys.json")))
-    for name, cfg in (("CDM", cdm_model_cfg(1024)), ("CMDM", cmdm_model_cfg(8192))):
+    for name, cfg, kname in (("CDM", cdm_model_cfg(1024), "CDM"), ("CMDM", cmdm_model_cfg(8192), "CMDM"),
+                             ("CDM", cdm_model_cfg(1024, use_scene_model=True), "CDM_scene")):
         m = Model.get(name)(cfg, device="cpu")
         mine = {k: list(v.shape) for k, v in m.state_dict().items()}
-        assert mine == keys[name], name
+        assert mine == keys[kname], kname
+        name = kname
         # buffers the reference computes deterministically are bit-identical
         sd = synth.fill_state_dict({k: tuple(v) for k, v in keys[name].items()}, seed=0)
         missing, unexpected = m.load_state_dict(sd, strict=False)

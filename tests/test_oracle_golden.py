@@ -150,3 +150,33 @@ def test_pointops_c_vs_numpy_and_fixture(golden_dir):
     i3, _ = pointops_ref.knnquery(8, xyz2, xyz2, o2, o2)
     assert (i3[:5, :5].numpy() < 5).all() and (i3[:5, 5:] == 0).all()
     assert (i3[5:].numpy() >= 5).all()
+
+
+@pytest.mark.parametrize("cdim", [3, 6])
+def test_scene_seg_oracle_matches_reference(golden_dir, cdim):
+    """Frozen PointTransformerSeg scene model: oracle restatement vs the reference module's own output."""
+    from oracle import scene_ref
+    g = _load(golden_dir, "scene_seg_b2_n1024.npz")
+    sd = synth.fill_state_dict(_keys(golden_dir)[f"PointTransformerSeg_c{cdim}"], seed=0)
+    B, N = 2, 1024
+    xyz = synth.scene_points(B, N, seed=51, dup_frac=0.05)
+    color = torch.rand(B, N, 3, generator=torch.Generator().manual_seed(51))
+    out = scene_ref.point_transformer_seg(sd, "", xyz, color, c=cdim)
+    assert out.shape == (B, N, 32)
+    err = np.abs(out.numpy() - g[f"feat_c{cdim}"]).max()
+    assert err < TOL, err
+
+
+def test_cdm_with_scene_model_oracle_matches_reference(golden_dir):
+    from oracle import scene_ref
+    g = _load(golden_dir, "scene_seg_b2_n1024.npz")
+    shapes = _keys(golden_dir)["CDM_scene"]
+    sd = _pe_buffers(synth.fill_state_dict(shapes, seed=0), {"timestep_embedder.pe": (1000, 128)})
+    B, N = 2, 1024
+    xyz = synth.scene_points(B, N, seed=51, dup_frac=0.05)
+    x = torch.randn(B, N, 6, generator=torch.Generator().manual_seed(52))
+    txt = synth.text_features(B, seed=51)
+    pf = scene_ref.point_transformer_seg(sd, "scene_model", xyz, None, c=3)
+    out = cdm_ref.cdm_forward(sd, x, torch.from_numpy(g["t"]), txt, xyz, point_feat=pf)
+    err = np.abs(out.numpy() - g["cdm_scene_out"]).max()
+    assert err < TOL, err
