@@ -34,22 +34,22 @@ def randn_(out: torch.Tensor, per_sample: int, nsample: int, sample0: int, seed:
     return out
 
 
-def p_sample_update(x0_hat, x_t, x_prev, noise, coef1, coef2, logvar, t, t_stride, seed=0, sample0=0):
+def p_sample_update(x0_hat, x_t, x_prev, noise, coef1, coef2, logvar, t, t_stride, seed=0, sample0=0, seed_dev=None):
     _chk_cuda(x0_hat, x_t, x_prev, t)
     B = x_t.shape[0]
     per = x_t.numel() // B
     _l.check(_l.load().am_p_sample_update(_ptr(_f32c(x0_hat)), _ptr(_f32c(x_t)), _ptr(x_prev), _ptr(noise), _ptr(coef1), _ptr(coef2),
-                                         _ptr(logvar), _ptr(t), t_stride, B, per, seed, sample0, _stream()), "am_p_sample_update")
+                                         _ptr(logvar), _ptr(t), t_stride, B, per, seed, _ptr(seed_dev), sample0, _stream()), "am_p_sample_update")
     return x_prev
 
 
-def ddim_update(x0_hat, x_t, x_prev, noise, sqrt_recip_ac, sqrt_recipm1_ac, ac, ac_prev, eta, t, t_stride, seed=0, sample0=0):
+def ddim_update(x0_hat, x_t, x_prev, noise, sqrt_recip_ac, sqrt_recipm1_ac, ac, ac_prev, eta, t, t_stride, seed=0, sample0=0, seed_dev=None):
     _chk_cuda(x0_hat, x_t, x_prev, t)
     B = x_t.shape[0]
     per = x_t.numel() // B
     _l.check(_l.load().am_ddim_update(_ptr(_f32c(x0_hat)), _ptr(_f32c(x_t)), _ptr(x_prev), _ptr(noise), _ptr(sqrt_recip_ac),
                                      _ptr(sqrt_recipm1_ac), _ptr(ac), _ptr(ac_prev), float(eta), _ptr(t), t_stride, B, per, seed,
-                                     sample0, _stream()), "am_ddim_update")
+                                     _ptr(seed_dev), sample0, _stream()), "am_ddim_update")
     return x_prev
 
 

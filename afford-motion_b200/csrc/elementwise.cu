@@ -51,7 +51,8 @@ __global__ void sampler_update_kernel(const float* __restrict__ x0_hat, const fl
                                       const float* __restrict__ noise, const float* __restrict__ c0, const float* __restrict__ c1,
                                       const float* __restrict__ c2, const float* __restrict__ c3, float eta,
                                       const int32_t* __restrict__ t, int t_stride, int B, int64_t per_sample, uint64_t seed,
-                                      int64_t sample0, int vec_ok) {
+                                      const uint64_t* __restrict__ seed_dev, int64_t sample0, int vec_ok) {
+    if (seed_dev) seed = *seed_dev;
     int64_t nblk = (per_sample + 3) / 4;
     int64_t total = nblk * B;
     for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
@@ -175,26 +176,26 @@ extern "C" int am_randn(float* out, int64_t per_sample, int nsample, int64_t sam
 
 extern "C" int am_p_sample_update(const float* x0_hat, const float* x_t, float* x_prev, const float* noise, const float* coef1,
                                   const float* coef2, const float* logvar, const int32_t* t, int t_stride, int B, int64_t per_sample,
-                                  uint64_t seed, int64_t sample0, am_stream_t stream) {
+                                  uint64_t seed, const uint64_t* seed_dev, int64_t sample0, am_stream_t stream) {
     AM_REQUIRE(x0_hat && x_t && x_prev && coef1 && coef2 && logvar && t, AM_EINVAL, "am_p_sample_update: null pointer");
     AM_REQUIRE(B > 0 && per_sample > 0 && (t_stride == 0 || t_stride == 1), AM_EINVAL, "am_p_sample_update: bad dims");
     int vec_ok = (per_sample % 4 == 0) && aligned16(x0_hat) && aligned16(x_t) && aligned16(x_prev) && (!noise || aligned16(noise));
     int64_t items = ((per_sample + 3) / 4) * B;
     sampler_update_kernel<0><<<ew_grid(items), EW_THREADS, 0, as_stream(stream)>>>(x0_hat, x_t, x_prev, noise, coef1, coef2, logvar, nullptr,
-                                                                                   0.f, t, t_stride, B, per_sample, seed, sample0, vec_ok);
+                                                                                   0.f, t, t_stride, B, per_sample, seed, seed_dev, sample0, vec_ok);
     AM_LAUNCH_CHECK("p_sample_update");
     return AM_OK;
 }
 
 extern "C" int am_ddim_update(const float* x0_hat, const float* x_t, float* x_prev, const float* noise, const float* sqrt_recip_ac,
                               const float* sqrt_recipm1_ac, const float* ac, const float* ac_prev, float eta, const int32_t* t,
-                              int t_stride, int B, int64_t per_sample, uint64_t seed, int64_t sample0, am_stream_t stream) {
+                              int t_stride, int B, int64_t per_sample, uint64_t seed, const uint64_t* seed_dev, int64_t sample0, am_stream_t stream) {
     AM_REQUIRE(x0_hat && x_t && x_prev && sqrt_recip_ac && sqrt_recipm1_ac && ac && ac_prev && t, AM_EINVAL, "am_ddim_update: null pointer");
     AM_REQUIRE(B > 0 && per_sample > 0 && (t_stride == 0 || t_stride == 1), AM_EINVAL, "am_ddim_update: bad dims");
     int vec_ok = (per_sample % 4 == 0) && aligned16(x0_hat) && aligned16(x_t) && aligned16(x_prev) && (!noise || aligned16(noise));
     int64_t items = ((per_sample + 3) / 4) * B;
     sampler_update_kernel<1><<<ew_grid(items), EW_THREADS, 0, as_stream(stream)>>>(x0_hat, x_t, x_prev, noise, sqrt_recip_ac, sqrt_recipm1_ac,
-                                                                                   ac, ac_prev, eta, t, t_stride, B, per_sample, seed, sample0, vec_ok);
+                                                                                   ac, ac_prev, eta, t, t_stride, B, per_sample, seed, seed_dev, sample0, vec_ok);
     AM_LAUNCH_CHECK("ddim_update");
     return AM_OK;
 }

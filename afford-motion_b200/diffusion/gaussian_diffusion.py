@@ -281,71 +281,104 @@ class GaussianDiffusion:
 
     # ------------------------------------------------------------------ device-resident loop (CUDA graph per step)
     def _fast_loop(self, kind, model, img, model_kwargs, eta, seed, progress, only_final, use_graph=True, step_noise=None):
-        """x_t, the timestep and all tables stay on the device; one captured graph = one denoise step
-        (network evaluation + fused sampler update + timestep decrement), replayed num_timesteps times."""
+        """x_t, the timestep, the Philox key and all tables stay on the device; one captured graph = `unroll` consecutive
+        denoise steps (network evaluation + fused sampler update + timestep decrement), replayed until t reaches 0.
+
+        The loop state (x_t / x0_hat / timestep / seed buffers and the captured graph) is a PLAN kept on the model's
+        persistent sampler handle, so every later job of the same shape replays the graph captured by the first one:
+        measured on B200, re-capturing per job cost 10 ms typically but 200-1000 ms sporadically (graph instantiate +
+        private-pool alloc/free, profiles/r1_job_timeline_before_graph_cache.txt)."""
         device = img.device
         tab = self._tables(device)
         tmap = getattr(self, "timestep_map", list(range(self.num_timesteps)))
+        import time as _time
+        trace = getattr(self, "trace", None)  # tools/job_timeline.py: list that receives (label, host perf_counter) pairs
+
+        def _tr(label):
+            if trace is not None:
+                trace.append((label, _time.perf_counter()))
+        _tr("loop_begin")
         with th.no_grad():
             handle = model.sampler_begin(tuple(img.shape), model_kwargs, tmap)
-            B = img.shape[0]
-            x0 = th.empty_like(img)
-            t_dev = th.full((1,), self.num_timesteps - 1, device=device, dtype=th.int32)
+            _tr("sampler_begin_done")
+            n = self.num_timesteps
+            plans = getattr(handle, "plans", None)
+            reuse = plans is not None and use_graph and only_final and step_noise is None
+            pkey = (kind, float(eta), int(self.sample_offset), n, id(tab))
+            plan = plans.get(pkey) if reuse else None
+            if plan is None:
+                plan = {"img": th.empty_like(img) if reuse else img, "x0": th.empty_like(img),
+                        "t": th.empty(1, device=device, dtype=th.int32), "seed": th.empty(1, device=device, dtype=th.int64),
+                        "graph": None, "unroll": 1, "per_graph": 0, "tab": tab}  # `tab` pinned: the graph bakes its pointers
+                if reuse:
+                    plans[pkey] = plan
+            if plan["img"] is not img:
+                plan["img"].copy_(img)
+                img = plan["img"]
+            x0, t_dev, seed_dev = plan["x0"], plan["t"], plan["seed"]
+            t_dev.fill_(n - 1)
+            seed_dev.fill_(int(seed))
 
             def one_step(nz=None):
                 handle.forward(img, t_dev, x0)
                 if kind == "ddpm":
-                    ops.p_sample_update(x0, img, img, nz, tab["coef1"], tab["coef2"], tab["logvar"], t_dev, 0, seed=seed, sample0=self.sample_offset)
+                    ops.p_sample_update(x0, img, img, nz, tab["coef1"], tab["coef2"], tab["logvar"], t_dev, 0, seed_dev=seed_dev,
+                                        sample0=self.sample_offset)
                 else:
                     ops.ddim_update(x0, img, img, nz, tab["sqrt_recip_ac"], tab["sqrt_recipm1_ac"], tab["ac"], tab["ac_prev"], eta,
-                                    t_dev, 0, seed=seed, sample0=self.sample_offset)
+                                    t_dev, 0, seed_dev=seed_dev, sample0=self.sample_offset)
                 ops.add_i32(t_dev, -1)
 
-            n = self.num_timesteps
-            graph, unroll = None, 1
             from amb200 import lib as _lib
-            launches0, per_graph, replays = _lib.launch_count(), 0, 0
+            launches0, replays, captured_now = _lib.launch_count(), 0, 0
             pbar = None
             if progress:
                 from tqdm.auto import tqdm
                 pbar = tqdm(total=n)
             k = 0
             while k < n:
+                done = 0
                 if step_noise is not None:  # parity harness: injected eps, eager
                     one_step(step_noise(k))
                     done = 1
-                elif k == 0 or not use_graph or not only_final and unroll > 1:
-                    one_step()  # eager first step: allocates every workspace before capture
+                elif not use_graph:
+                    one_step()
                     done = 1
+                elif plan["graph"] is None and k == 0:
+                    one_step()  # eager first step of the first job: allocates every workspace before capture
+                    done = 1
+                elif plan["graph"] is None:
+                    # one captured graph = `unroll` consecutive denoise steps (fewer host launches per job: the loop is
+                    # host-driven, and a stalled host thread would idle the GPU)
+                    plan["unroll"] = 8 if (only_final and n - k >= 64) else 1
+                    _tr("eager_step_enqueued")
+                    th.cuda.synchronize(device)
+                    _tr("pre_capture_sync_done")
+                    _t0 = _time.perf_counter()
+                    graph = th.cuda.CUDAGraph()
+                    c0 = _lib.launch_count()
+                    with th.cuda.graph(graph):
+                        for _ in range(plan["unroll"]):
+                            one_step()
+                    plan["per_graph"] = captured_now = _lib.launch_count() - c0
+                    plan["graph"] = graph  # capture records without executing: the captured steps still have to run
+                    self.last_capture_ms = 1e3 * (_time.perf_counter() - _t0)  # host cost of capture + instantiate
+                    _tr("capture_done")
+                elif n - k >= plan["unroll"]:
+                    plan["graph"].replay()
+                    replays += 1
+                    done = plan["unroll"]
                 else:
-                    if graph is None:
-                        # one captured graph = `unroll` consecutive denoise steps (fewer host launches per job: the loop is
-                        # host-driven, and a stalled host thread would idle the GPU)
-                        unroll = 8 if (only_final and n - k >= 64) else 1
-                        th.cuda.synchronize(device)
-                        import time as _time
-                        _t0 = _time.perf_counter()
-                        graph = th.cuda.CUDAGraph()
-                        c0 = _lib.launch_count()
-                        with th.cuda.graph(graph):
-                            for _ in range(unroll):
-                                one_step()
-                        per_graph = _lib.launch_count() - c0
-                        self.last_capture_ms = 1e3 * (_time.perf_counter() - _t0)  # host cost of capture + instantiate (per job)
-                        # capture records without executing: the captured steps still have to run
-                    if n - k >= unroll:
-                        graph.replay()
-                        replays += 1
-                        done = unroll
-                    else:
-                        one_step()  # tail shorter than the captured graph
-                        done = 1
+                    one_step()  # tail shorter than the captured graph
+                    done = 1
                 k += done
-                if pbar is not None:
+                if k >= n:
+                    _tr("all_enqueued")
+                if pbar is not None and done:
                     pbar.update(done)
-                self.last_launches = (_lib.launch_count() - launches0 - (per_graph if graph is not None else 0)) + per_graph * replays
-                if not only_final or k >= n:
-                    last = k >= n
+                self.last_launches = (_lib.launch_count() - launches0 - captured_now) + plan["per_graph"] * replays
+                if done and (not only_final or k >= n):
+                    last = k >= n and not reuse  # plan buffers are overwritten by the next job: hand out copies
                     yield {"sample": img if last else img.clone(), "pred_xstart": x0 if last else x0.clone()}
 
     # ------------------------------------------------------------------ training

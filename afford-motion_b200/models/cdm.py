@@ -135,14 +135,43 @@ class CDM(nn.Module):
         return self.engine.forward(x.float().contiguous(), t_dev, 1, cond)
 
     def sampler_begin(self, shape, model_kwargs, timestep_map):
-        """Device-resident sampling hook used by diffusion.gaussian_diffusion._fast_loop."""
+        """Device-resident sampling hook used by diffusion.gaussian_diffusion._fast_loop.  The handle is persistent per
+        (shape, timestep map, weight version): later jobs copy their conditioning into its buffers and replay its graph."""
         cond = self.encode_condition(**model_kwargs)
         eng = self.engine
-        tmap = torch.tensor(list(timestep_map), device=cond.xyz.device, dtype=torch.long)
-        table = eng.w["time_table"][tmap].contiguous()
+        pf = cond.point_feat
+        key = (tuple(shape), tuple(timestep_map), eng._version, None if pf is None else tuple(pf.shape), str(cond.xyz.device))
+        handles = self.__dict__.setdefault("_sampler_handles", {})
+        h = handles.get(key)
+        if h is None:
+            if len(handles) >= 8:
+                handles.clear()
+            h = handles[key] = _CDMSamplerHandle(eng, cond, timestep_map)
+        h.rebind(cond)
+        return h
 
-        class _Handle:
-            @staticmethod
-            def forward(x, t_dev, out):
-                return eng.forward(x, t_dev, 0, cond, out=out, time_table=table)
-        return _Handle()
+
+class _CDMSamplerHandle:
+    """Persistent per-(shape, timestep map, weight version) sampling state; see CDM.sampler_begin."""
+
+    def __init__(self, eng, cond, timestep_map):
+        from amb200.cdm_engine import CDMCondition
+        dev = cond.xyz.device
+        idx = torch.as_tensor(list(timestep_map), dtype=torch.long).to(dev)
+        self.eng = eng
+        self.table = eng.w["time_table"][idx].contiguous()
+        self.cond = CDMCondition(B=cond.B, N=cond.N, xyz=torch.empty_like(cond.xyz), text_latent=torch.empty_like(cond.text_latent),
+                                 point_feat=None if cond.point_feat is None else torch.empty_like(cond.point_feat))
+        self.plans = {}
+
+    def rebind(self, cond):
+        self.cond.xyz.copy_(cond.xyz)
+        self.cond.text_latent.copy_(cond.text_latent)
+        if self.cond.point_feat is not None:
+            self.cond.point_feat.copy_(cond.point_feat)
+        ws = self.eng.workspace(cond.B, cond.N, cond.xyz.device)
+        ws["L0"][:, 0, :].copy_(self.cond.text_latent)
+        ws["cond_id"] = self.cond
+
+    def forward(self, x, t_dev, out):
+        return self.eng.forward(x, t_dev, 0, self.cond, out=out, time_table=self.table)

@@ -114,15 +114,45 @@ class CMDM(nn.Module):
         return self.engine.forward(x.float().contiguous(), t_dev, 1, cond)
 
     def sampler_begin(self, shape, model_kwargs, timestep_map):
-        """Device-resident sampling hook used by diffusion.gaussian_diffusion._fast_loop: conditioning encoded once,
-        time-token table re-indexed by the (respaced) timestep map so the device timestep indexes it directly."""
+        """Device-resident sampling hook used by diffusion.gaussian_diffusion._fast_loop: conditioning encoded once per job and
+        bound into the engine's persistent token buffer; the handle itself (re-indexed time-token table, key-padding buffer,
+        loop plans with their captured CUDA graph) is PERSISTENT per (shape, timestep map, weight version), so later jobs of
+        the same shape replay the first job's graph."""
         cond = self.encode_condition(shape[1], **model_kwargs)
         eng = self.engine
-        tmap = torch.tensor(list(timestep_map), device=cond.static_tokens.device, dtype=torch.long)
-        table = eng.w["time_table"][tmap].contiguous()
+        key = (tuple(shape), tuple(timestep_map), eng._version, cond.key_pad is None, cond.G, str(cond.static_tokens.device))
+        handles = self.__dict__.setdefault("_sampler_handles", {})
+        h = handles.get(key)
+        if h is None:
+            if len(handles) >= 8:  # each handle pins a captured graph and its memory pool
+                handles.clear()
+            h = handles[key] = _CMDMSamplerHandle(eng, cond, timestep_map)
+        h.rebind(cond)
+        return h
 
-        class _Handle:
-            @staticmethod
-            def forward(x, t_dev, out):
-                return eng.forward(x, t_dev, 0, cond, out=out, time_table=table)
-        return _Handle()
+
+class _CMDMSamplerHandle:
+    """Persistent per-(shape, timestep map, weight version) sampling state; see CMDM.sampler_begin."""
+
+    def __init__(self, eng, cond, timestep_map):
+        from amb200.cmdm_engine import CMDMCondition
+        dev = cond.static_tokens.device
+        idx = torch.as_tensor(list(timestep_map), dtype=torch.long).to(dev)  # once per handle (a pageable H2D copy synchronises)
+        self.eng = eng
+        self.table = eng.w["time_table"][idx].contiguous()
+        self.cond = CMDMCondition(B=cond.B, G=cond.G, T=cond.T, static_tokens=cond.static_tokens,
+                                  key_pad=None if cond.key_pad is None else torch.empty_like(cond.key_pad))
+        self.plans = {}
+
+    def rebind(self, cond):
+        """New job: copy its conditioning into the buffers the captured graph reads."""
+        ws = self.eng.workspace(cond.B, 2 + cond.G + cond.T, cond.static_tokens.device)
+        ws["cond_id"] = None
+        self.eng.bind_condition(ws, cond)
+        if self.cond.key_pad is not None:
+            self.cond.key_pad.copy_(cond.key_pad)
+        self.cond.static_tokens = cond.static_tokens
+        ws["cond_id"] = self.cond
+
+    def forward(self, x, t_dev, out):
+        return self.eng.forward(x, t_dev, 0, self.cond, out=out, time_table=self.table)

@@ -59,11 +59,12 @@ int am_randn(float* out, int64_t per_sample, int nsample, int64_t sample0, uint6
 /* p_sample, START_X + FIXED_SMALL, clip_denoised=False (gaussian_diffusion.py:209-231,306-315,396-440):
  *   x_prev = coef1[t]*x0_hat + coef2[t]*x_t + (t!=0) * exp(0.5*logvar[t]) * eps
  * eps = noise[...] when noise != NULL, else in-kernel Philox(seed, subseq = t, sample0 + b).
- * x_prev may alias x_t. */
+ * seed_dev (nullable): when non-NULL the Philox key is read from device memory (*seed_dev) instead of `seed`, so a
+ * captured CUDA graph of the step can be replayed for a later job with a new seed.  x_prev may alias x_t. */
 int am_p_sample_update(const float* x0_hat, const float* x_t, float* x_prev, const float* noise,
                        const float* coef1, const float* coef2, const float* logvar, const int32_t* t,
-                       int t_stride, int B, int64_t per_sample, uint64_t seed, int64_t sample0,
-                       am_stream_t stream);
+                       int t_stride, int B, int64_t per_sample, uint64_t seed, const uint64_t* seed_dev,
+                       int64_t sample0, am_stream_t stream);
 
 /* ddim_sample (gaussian_diffusion.py:346-350,538-586):
  *   eps = (sqrt_recip_ac[t]*x_t - x0_hat)/sqrt_recipm1_ac[t]; sigma = eta*sqrt((1-acp)/(1-ac))*sqrt(1-ac/acp)
@@ -71,7 +72,8 @@ int am_p_sample_update(const float* x0_hat, const float* x_t, float* x_prev, con
 int am_ddim_update(const float* x0_hat, const float* x_t, float* x_prev, const float* noise,
                    const float* sqrt_recip_ac, const float* sqrt_recipm1_ac, const float* ac,
                    const float* ac_prev, float eta, const int32_t* t, int t_stride, int B,
-                   int64_t per_sample, uint64_t seed, int64_t sample0, am_stream_t stream);
+                   int64_t per_sample, uint64_t seed, const uint64_t* seed_dev, int64_t sample0,
+                   am_stream_t stream);
 
 /* q_sample (gaussian_diffusion.py:189-207): x_t = sqrt_ac[t]*x0 + sqrt_1mac[t]*noise  (t per sample) */
 int am_q_sample(const float* x0, const float* noise, float* x_t, const float* sqrt_ac,
