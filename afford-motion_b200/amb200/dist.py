@@ -56,3 +56,15 @@ def gather_samples(local: torch.Tensor, global_batch: int) -> Optional[List[torc
         bufs = [None] * world
         dist.all_gather_object(bufs, local.cpu())
     return bufs if rank == 0 else None
+
+
+def allreduce_flat_(bufs: List[torch.Tensor], group=None) -> int:
+    """In-place SUM all-reduce of flat gradient buffers (training exchange step); returns the world size the
+    caller divides by (amb200.optim.FusedAdamW folds 1/world into its update kernel).  No-op for a single process."""
+    if not dist.is_initialized():
+        return 1
+    world = dist.get_world_size(group)
+    if world > 1:
+        for b in bufs:
+            dist.all_reduce(b, op=dist.ReduceOp.SUM, group=group)
+    return world

@@ -264,6 +264,14 @@ int am_maxpool_k_bwd(const float* dout, const int32_t* arg, float* dZ, int64_t m
 int am_masked_mse_bwd(const float* x0, const float* pred, const uint8_t* mask, const float* gloss, float* dpred, int B, int T, int D,
                       am_stream_t stream);
 
+/* ------------------------------------------------------------------ optimiser (utils/training.py:48-50,139,154)
+ * Fused flat-buffer AdamW == torch.optim.AdamW(lr, betas, eps, weight_decay) applied to every parameter in ONE launch:
+ *   g' = g*grad_scale;  p *= 1 - lr*wd;  m = b1*m + (1-b1)*g';  v = b2*v + (1-b2)*g'^2;
+ *   p -= lr/(1-b1^step) * m / (sqrt(v)/sqrt(1-b2^step) + eps);   step >= 1 is the 1-based update count.
+ * zero_grad != 0 also clears g (the next step's optimizer.zero_grad()).  All four buffers: fp32, n elements, 16-byte aligned. */
+int am_adamw_flat(float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, int64_t step, float grad_scale, int zero_grad, am_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

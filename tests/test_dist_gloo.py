@@ -28,7 +28,11 @@ def _worker(rank, world, port, q):
     if (e - s) != 33 // w:  # uneven shards: equalise for the tensor all_gather used on the happy path
         local = local[: 33 // w]
     got = D.gather_samples(local, (33 // w) * w)
-    q.put((r, (s, e), slow, None if got is None else torch.cat(got).tolist()))
+    # training exchange step: SUM all-reduce of a flat gradient buffer + the 1/world scale the fused AdamW folds in
+    flat = [torch.full((10,), float(r + 1)), torch.arange(4, dtype=torch.float32) * (r + 1)]
+    wsz = D.allreduce_flat_(flat)
+    mean_ok = wsz == w and torch.allclose(flat[0] / wsz, torch.full((10,), 1.5)) and torch.allclose(flat[1] / wsz, torch.arange(4.0) * 1.5)
+    q.put((r, (s, e), slow, None if got is None else torch.cat(got).tolist(), bool(mean_ok)))
     import torch.distributed as dist
     dist.destroy_process_group()
 
@@ -42,7 +46,8 @@ def test_two_rank_gloo_plumbing():
     res = sorted(q.get(timeout=120) for _ in range(world))
     [p.join(60) for p in ps]
     assert all(p.exitcode == 0 for p in ps)
-    (r0, sh0, slow0, g0), (r1, sh1, slow1, g1) = res
+    (r0, sh0, slow0, g0, ok0), (r1, sh1, slow1, g1, ok1) = res
+    assert ok0 and ok1                                     # flat gradient all-reduce gives the mean on every rank
     assert sh0 == (0, 17) and sh1 == (17, 33)            # contiguous, exhaustive, sizes differ by <= 1
     assert slow0 == slow1 == 15.0                          # max over ranks on every rank
     assert g1 is None and len(g0) == 32 and g0[0] == [0.0, 0.0, 0.0] and g0[16][0] == 17.0

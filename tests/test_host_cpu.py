@@ -106,3 +106,23 @@ def test_text_provider_hook_and_missing_clip():
     assert torch.equal(F.encode_text_clip(m, ["a", "b"]), feats)
     F.set_text_feature_provider(None)
     assert F.get_lang_feat_dim_type("ViT-B/32") == (512, "clip")
+
+
+def test_adamw_oracle_matches_torch_optim():
+    """Pins oracle/optim_ref.py against torch.optim.AdamW (what utils/training.py:48 constructs) on CPU, incl. weight decay."""
+    from oracle.optim_ref import adamw_step
+    g = torch.Generator().manual_seed(0)
+    p0 = [torch.randn(33, 7, generator=g), torch.randn(5, generator=g)]
+    params = [torch.nn.Parameter(t.clone()) for t in p0]
+    opt = torch.optim.AdamW(params, lr=3e-3, weight_decay=0.02)
+    mine = [t.clone() for t in p0]
+    m = [torch.zeros_like(t) for t in p0]
+    v = [torch.zeros_like(t) for t in p0]
+    for step in range(1, 6):
+        grads = [torch.randn(t.shape, generator=g) for t in p0]
+        for q, gr in zip(params, grads):
+            q.grad = gr.clone()
+        opt.step()
+        for i in range(2):
+            adamw_step(mine[i], grads[i], m[i], v[i], step, lr=3e-3, weight_decay=0.02)
+            assert torch.allclose(mine[i], params[i].data, rtol=0, atol=1e-7), (step, i)
