@@ -14,7 +14,7 @@ REPO_ROOT = os.path.dirname(PKG_ROOT)
 LIB_PATH = os.path.join(PKG_ROOT, "csrc", "libamb200.so")
 HEADER_PATH = os.path.join(REPO_ROOT, "include", "amb200.h")
 
-_CT = {"int": c_int, "int32_t": c_int32, "int64_t": c_int64, "uint64_t": c_uint64, "uint32_t": ctypes.c_uint32, "float": c_float,
+_CT = {"double": ctypes.c_double, "int": c_int, "int32_t": c_int32, "int64_t": c_int64, "uint64_t": c_uint64, "uint32_t": ctypes.c_uint32, "float": c_float,
        "am_stream_t": c_void_p}
 
 

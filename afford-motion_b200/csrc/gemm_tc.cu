@@ -458,6 +458,103 @@ __device__ __forceinline__ void epilogue_tile_tma(const TcParams& p, const CUten
     }
 }
 
+// TMA-load + TMA-store epilogue for fp32 outputs (MODE 4: out_proj / FFN2 / CDM per-point MLP — bias (+act) (+ fp32 residual)).
+// The LSU path (MODE 2) makes these GEMMs epilogue-bound: per 32x32 block every lane waits for 8 residual loads and issues 8
+// global stores, and those stores also slow the main loop (see MODE 3).  Here the residual arrives through the TMA engine one
+// half-block AHEAD (two 2 KB ping-pong buffers per warp; the first load of a tile is issued before its accumulator is ready)
+// and the result leaves through a TMA store from the same buffer:
+//   tcgen05.ld (lane = row, 16 columns) -> + bias (+act) -> + residual from smem -> st.shared in place -> TMA store.
+// Half-block = 32 rows x 16 fp32 columns = 64-byte rows, SWIZZLE_64B (chunk c of row r at c ^ ((r >> 1) & 3)): conflict-free
+// for one-row-per-lane accesses.  Rows >= M are zero-filled on load and clipped on store by the tensor maps.
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (true) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) break;
+        if (++spins > 200000000u) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d_s(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+
+template <int ACT, int NCOLS>
+__device__ __forceinline__ void epilogue_tile_tma_f32(const TcParams& p, const CUtensorMap* tmYf, const CUtensorMap* tmR, uint32_t tmem_tile,
+                                                      int m0, int n0, int q, int half, int lane, uint32_t buf_u32 /* 2 x 2 KB */,
+                                                      uint32_t bar_u32 /* 2 mbarriers */, uint32_t& phases, uint64_t* tmem_full_bar,
+                                                      uint32_t tmem_full_parity) {
+    constexpr int NHB = NCOLS / 32;  // 16-column half-blocks owned by this warp
+    const int m_base = m0 + q * 32;
+    const bool rows_ok = m_base < p.M;
+    const bool has_res = p.residual != nullptr;
+    const int ncol0 = n0 + half * (NCOLS / 2);
+    if (rows_ok && has_res && lane == 0) {
+        // residual of half-block 0, issued while this tile's main loop may still be running; buffer 0 was last read by the
+        // bulk store two groups back
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        tma_load_2d_s(buf_u32, tmR, bar_u32, ncol0, m_base, 2048);
+    }
+    mbar_wait(tmem_full_bar, tmem_full_parity);
+    tc_fence_after();
+    if (!rows_ok) return;
+#pragma unroll 1
+    for (int j = 0; j < NHB; ++j) {
+        const int b = j & 1;
+        const uint32_t buf = buf_u32 + (uint32_t)b * 2048u;
+        const int n = ncol0 + j * 16;
+        uint32_t v[16];
+        tmem_ld16(tmem_tile + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (NCOLS / 2) + j * 16), v);
+        float f[16];
+#pragma unroll
+        for (int c = 0; c < 16; c += 4) {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + c));
+            f[c] = act_ct<ACT>(__uint_as_float(v[c]) + b4.x); f[c + 1] = act_ct<ACT>(__uint_as_float(v[c + 1]) + b4.y);
+            f[c + 2] = act_ct<ACT>(__uint_as_float(v[c + 2]) + b4.z); f[c + 3] = act_ct<ACT>(__uint_as_float(v[c + 3]) + b4.w);
+        }
+        if (lane == 0) {
+            if (has_res && j + 1 < NHB) {
+                // the other buffer was read by the most recent bulk store: wait for that read, then prefetch the next residual
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                tma_load_2d_s(buf_u32 + (uint32_t)(b ^ 1) * 2048u, tmR, bar_u32 + (uint32_t)(b ^ 1) * 8u, n + 16, m_base, 2048);
+            } else {
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // this buffer's previous store (two groups back) is done reading
+            }
+        }
+        __syncwarp();
+        const uint32_t rowa = buf + (uint32_t)lane * 64u;
+        const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+        if (has_res) {
+            mbar_wait_s(bar_u32 + (uint32_t)b * 8u, (phases >> b) & 1u);
+            phases ^= (1u << b);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float r0, r1, r2, r3;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r0), "=f"(r1), "=f"(r2), "=f"(r3) : "r"(rowa + (((uint32_t)c ^ sw) << 4)) : "memory");
+                f[4 * c] += r0; f[4 * c + 1] += r1; f[4 * c + 2] += r2; f[4 * c + 3] += r3;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + (((uint32_t)c ^ sw) << 4)), "f"(f[4 * c]), "f"(f[4 * c + 1]), "f"(f[4 * c + 2]), "f"(f[4 * c + 3]) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                         ::"l"(reinterpret_cast<uint64_t>(tmYf)), "r"(buf), "r"(n), "r"(m_base) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+}
+
 template <int BK, int STAGES, int MINB, int ACT>
 __global__ void __launch_bounds__(TC_THREADS, MINB)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
@@ -556,7 +653,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <int BN_, int NST, int ACT, int MODE>
 __global__ void __launch_bounds__(TCP_THREADS, 1)
 gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                          const __grid_constant__ CUtensorMap tmY, TcParams p, int n_tiles, int total_tiles) {
+                          const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR, TcParams p, int n_tiles,
+                          int total_tiles) {
     constexpr int BK = 32;
     constexpr int A_SUB = BM * BK * 2;          // 8 KB
     constexpr int B_SUB = BN_ * BK * 2;         // 8 / 16 KB
@@ -570,6 +668,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     uint64_t* tmem_empty = tmem_full + 2;  // [2]
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
     float* stage_buf = reinterpret_cast<float*>(smem + NST * STAGE_BYTES + 1024);  // 8 warps x 4 KB (epilogue transpose / TMA-store tiles), 1024-aligned
+    uint64_t* epi_bars = reinterpret_cast<uint64_t*>(smem + NST * STAGE_BYTES + 512);  // [8 warps][2]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = p.Kp / BK;
@@ -586,6 +685,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     if (warp == MMA_WARP && lane == 0) {
         for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 256); }
+        for (int i = 0; i < 16; ++i) mbar_init(&epi_bars[i], 1);  // MODE 4: two residual-load barriers per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -648,9 +748,18 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         // ===================== epilogue (overlaps the next tile's main loop) =====================
         const int q = warp & 3, half = warp >> 2;
         int it = 0;
+        uint32_t epi_phases = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int ab = it & 1;
             const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN_;
+            if (MODE == 4) {
+                epilogue_tile_tma_f32<ACT, BN_>(p, &tmY, &tmR, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane,
+                                                smem_u32(stage_buf + warp * (32 * 32)), smem_u32(epi_bars + warp * 2), epi_phases,
+                                                &tmem_full[ab], (uint32_t)((it >> 1) & 1));
+                tc_fence_before();
+                mbar_arrive(&tmem_empty[ab]);
+                continue;
+            }
             mbar_wait(&tmem_full[ab], (it >> 1) & 1);
             tc_fence_after();
             if (dbg && threadIdx.x == 0 && it < 16) p.dbg[40 + it] = clock64();
@@ -661,7 +770,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             mbar_arrive(&tmem_empty[ab]);
             if (dbg && threadIdx.x == 0 && it < 16) p.dbg[72 + it] = clock64();
         }
-        if (MODE == 3 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all bulk stores of this warp complete before exit
+        if ((MODE == 3 || MODE == 4) && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all bulk stores of this warp complete before exit
     }
     tc_fence_before();
     __syncthreads();
@@ -677,7 +786,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 template <int BN_, int NST, int ACT, int MODE>
 __global__ void __launch_bounds__(TCP_THREADS, 1)
 gemm_tc_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                          const __grid_constant__ CUtensorMap tmY, TcParams p, int n_tiles, int total_tiles) {
+                          const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR, TcParams p, int n_tiles,
+                          int total_tiles) {
     constexpr int BK = 32;
     constexpr int A_SUB = BM * BK * 2;          // 8 KB
     constexpr int B_SUB = BN_ * BK * 2;         // 8 / 16 KB
@@ -691,6 +801,7 @@ gemm_tc_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     uint64_t* tmem_empty = tmem_full + 2;  // [2]
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
     float* stage_buf = reinterpret_cast<float*>(smem + NST * STAGE_BYTES + 1024);  // 8 warps x 4 KB (epilogue transpose / TMA-store tiles), 1024-aligned
+    uint64_t* epi_bars = reinterpret_cast<uint64_t*>(smem + NST * STAGE_BYTES + 512);  // [8 warps][2]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = p.Kp / BK;
@@ -711,6 +822,7 @@ gemm_tc_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     if (warp == MMA_WARP && lane == 0) {
         for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 2); }  // empty: both CTAs' MMA commits
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 256); }
+        for (int i = 0; i < 16; ++i) mbar_init(&epi_bars[i], 1);  // MODE 4: two residual-load barriers per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -778,9 +890,18 @@ gemm_tc_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         // ===================== epilogue (overlaps the next tile's main loop) =====================
         const int q = warp & 3, half = warp >> 2;
         int it = 0;
+        uint32_t epi_phases = 0;
         for (int tile = cluster_id; tile < total_pairs; tile += num_clusters, ++it) {
             const int ab = it & 1;
             const int m0 = ((tile / n_tiles) * 2 + (int)cta_rank) * BM, n0 = (tile % n_tiles) * BN_;
+            if (MODE == 4) {
+                epilogue_tile_tma_f32<ACT, BN_>(p, &tmY, &tmR, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane,
+                                                smem_u32(stage_buf + warp * (32 * 32)), smem_u32(epi_bars + warp * 2), epi_phases,
+                                                &tmem_full[ab], (uint32_t)((it >> 1) & 1));
+                tc_fence_before();
+                mbar_arrive(&tmem_empty[ab]);
+                continue;
+            }
             mbar_wait(&tmem_full[ab], (it >> 1) & 1);
             tc_fence_after();
             if (dbg && threadIdx.x == 0 && it < 16) p.dbg[40 + it] = clock64();
@@ -791,13 +912,171 @@ gemm_tc_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             mbar_arrive(&tmem_empty[ab]);
             if (dbg && threadIdx.x == 0 && it < 16) p.dbg[72 + it] = clock64();
         }
-        if (MODE == 3 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all bulk stores of this warp complete before exit
+        if ((MODE == 3 || MODE == 4) && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all bulk stores of this warp complete before exit
     }
     tc_fence_before();
     __syncthreads();
     // neither CTA may exit while the peer can still multicast into its smem / arrive on its barriers
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
     if (warp == ALLOC_WARP) tmem_dealloc(tmem_base, 2 * BN_);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// CTA-pair kernel: tcgen05.mma.cta_group::2 (UMMA M = 256 across two SMs of a TPC).
+// The 1-SM kernels above are SHARED-MEMORY-BANDWIDTH bound, not tensor bound: with the 3-term split every K16 step issues three
+// MMAs and each re-reads its A (4 KB) and B (8 KB at N=256) slices from smem — 96 B/clk — while the TMA engine writes 62 B/clk
+// of new operands and the epilogue stages 21 B/clk, against 128 B/clk of smem bandwidth (measured: 12.6K cycles per 128x256
+// tile alone, 17K with the epilogue running, 22K average; tile width, multicast and epilogue type make no difference —
+// profiles/r1_tc_tile_sweep.txt).  In a CTA pair each SM keeps only HALF of the W tile: the pair computes a 256 x BN tile,
+// SM r holds A rows [128r, 128r+128) and W rows [r*BN/2, (r+1)*BN/2), the tensor cores read the peer's half through the
+// pair's smem path.  Per SM: MMA reads 64 B/clk, TMA writes 42 B/clk, operand traffic from L2 drops by a third.
+//   * both CTAs: TMA producer (own A tile, own W half) — completion is signalled on the LEADER's `full` barrier
+//     (cp.async.bulk.tensor .cta_group::2, leader expects 2 x STAGE bytes); epilogue of the own 128 x BN accumulator
+//   * leader CTA (rank 0) only: one thread issues the MMAs; tcgen05.commit multicasts the stage release / accumulator-ready
+//     arrives to both CTAs; the peer's epilogue threads arrive remotely on the leader's `tmem_empty`
+template <int BN_, int NST, int ACT, int MODE, int BK>
+__global__ void __launch_bounds__(TCP_THREADS, 1)
+gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR, TcParams p, int n_tiles,
+                   int total_pairs) {
+    // BK = 32: 64-byte operand rows (SWIZZLE_64B); BK = 64: 128-byte rows (SWIZZLE_128B)
+    constexpr int A_SUB = BM * BK * 2;            // this CTA's 128 rows of A (hi or lo)
+    constexpr int B_SUB = (BN_ / 2) * BK * 2;     // this CTA's half of the W tile (hi or lo)
+    constexpr int STAGE_BYTES = 2 * A_SUB + 2 * B_SUB;
+    constexpr uint32_t IDESC_P = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN_ >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + NST * STAGE_BYTES);
+    uint64_t* empty = full + NST;
+    uint64_t* tmem_full = empty + NST;     // [2]
+    uint64_t* tmem_empty = tmem_full + 2;  // [2]  (used in the leader CTA only)
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* stage_buf = reinterpret_cast<float*>(smem + NST * STAGE_BYTES + 1024);
+    uint64_t* epi_bars = reinterpret_cast<uint64_t*>(smem + NST * STAGE_BYTES + 512);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkb = p.Kp / BK;
+    uint32_t cta_rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+    const bool leader = cta_rank == 0;
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+    if (warp == PRODUCER_WARP && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    }
+    if (warp == MMA_WARP && lane == 0) {
+        for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 512); }  // both CTAs' 256 epilogue threads
+        for (int i = 0; i < 16; ++i) mbar_init(&epi_bars[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == ALLOC_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"((uint32_t)(2 * BN_)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+    const bool dbg = p.dbg && blockIdx.x == 0;
+    if (dbg && threadIdx.x == 0) p.dbg[0] = clock64();
+
+    if (warp == PRODUCER_WARP) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            uint32_t kbc = 0;
+            for (int tile = cluster_id; tile < total_pairs; tile += num_clusters) {
+                const int m0 = ((tile / n_tiles) * 2 + (int)cta_rank) * BM;
+                const int nh = (tile % n_tiles) * BN_ + (int)cta_rank * (BN_ / 2);
+                for (int kb = 0; kb < nkb; ++kb, ++kbc) {
+                    const int s = kbc % NST;
+                    mbar_wait(&empty[s], ((kbc / NST) & 1) ^ 1);   // released in both CTAs by the leader's commit multicast
+                    const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
+                    uint32_t lbar;  // the LEADER's full[s] in the cluster shared window
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(lbar) : "r"(smem_u32(&full[s])), "r"(0u));
+                    if (leader) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full[s])), "r"((uint32_t)(2 * STAGE_BYTES)) : "memory");
+#define AM_TMA_2SM(dst_, map_, c0_, c1_)                                                                                              \
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" \
+                 ::"r"(dst_), "l"(reinterpret_cast<uint64_t>(map_)), "r"(lbar), "r"(c0_), "r"(c1_) : "memory")
+                    AM_TMA_2SM(st, &tmA, kb * BK, m0);                               // A_hi (own 128 rows)
+                    AM_TMA_2SM(st + A_SUB, &tmA, p.Kp + kb * BK, m0);                // A_lo
+                    AM_TMA_2SM(st + 2 * A_SUB, &tmB, kb * BK, nh);                   // W_hi, own half of the n-tile
+                    AM_TMA_2SM(st + 2 * A_SUB + B_SUB, &tmB, p.Kp + kb * BK, nh);    // W_lo
+#undef AM_TMA_2SM
+                }
+            }
+        }
+    } else if (warp == MMA_WARP) {
+        // ===================== MMA issuer: one thread of the LEADER CTA for the pair =====================
+        if (lane == 0 && leader) {
+            uint32_t kbc = 0;
+            int it = 0;
+            for (int tile = cluster_id; tile < total_pairs; tile += num_clusters, ++it) {
+                const int ab = it & 1;
+                mbar_wait(&tmem_empty[ab], (((it >> 1) & 1) ^ 1));
+                tc_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)(ab * BN_);
+                for (int kb = 0; kb < nkb; ++kb, ++kbc) {
+                    const int s = kbc % NST;
+                    mbar_wait(&full[s], (kbc / NST) & 1);   // both CTAs' operands of this stage have landed
+                    tc_fence_after();
+                    const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+                    const uint64_t a_hi = make_desc<BK>(base), a_lo = make_desc<BK>(base + A_SUB);
+                    const uint64_t w_hi = make_desc<BK>(base + 2 * A_SUB), w_lo = make_desc<BK>(base + 2 * A_SUB + B_SUB);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t ko = (uint64_t)(k * 2);
+#define AM_UMMA_2SM(a_, b_, acc_)                                                                                     \
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" \
+                 ::"r"(d), "l"(a_), "l"(b_), "r"(IDESC_P), "r"((uint32_t)(acc_)) : "memory")
+                        AM_UMMA_2SM(a_lo + ko, w_hi + ko, (kb | k) ? 1u : 0u);
+                        AM_UMMA_2SM(a_hi + ko, w_lo + ko, 1u);
+                        AM_UMMA_2SM(a_hi + ko, w_hi + ko, 1u);
+#undef AM_UMMA_2SM
+                    }
+                    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                                 ::"r"(smem_u32(&empty[s])), "h"((uint16_t)3) : "memory");
+                }
+                asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                             ::"r"(smem_u32(&tmem_full[ab])), "h"((uint16_t)3) : "memory");
+                if (dbg && it < 16) p.dbg[8 + it] = clock64();
+            }
+        }
+    } else if (warp < 8) {
+        // ===================== epilogue (both CTAs: own 128 x BN accumulator) =====================
+        const int q = warp & 3, half = warp >> 2;
+        int it = 0;
+        uint32_t epi_phases = 0;
+        for (int tile = cluster_id; tile < total_pairs; tile += num_clusters, ++it) {
+            const int ab = it & 1;
+            const int m0 = ((tile / n_tiles) * 2 + (int)cta_rank) * BM, n0 = (tile % n_tiles) * BN_;
+            uint32_t lempty;  // the leader's tmem_empty[ab]
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(lempty) : "r"(smem_u32(&tmem_empty[ab])), "r"(0u));
+            if (MODE == 4) {
+                epilogue_tile_tma_f32<ACT, BN_>(p, &tmY, &tmR, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane,
+                                                smem_u32(stage_buf + warp * (32 * 32)), smem_u32(epi_bars + warp * 2), epi_phases,
+                                                &tmem_full[ab], (uint32_t)((it >> 1) & 1));
+            } else {
+                mbar_wait(&tmem_full[ab], (it >> 1) & 1);
+                tc_fence_after();
+                if (MODE == 3) epilogue_tile_tma<ACT, BN_>(p, &tmY, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane, smem_u32(stage_buf + warp * (32 * 32)));
+                else if (MODE == 0) epilogue_tile_coalesced<ACT, BN_>(p, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane, stage_buf + warp * (32 * 32));
+                else epilogue_tile_fast<ACT, BN_, MODE>(p, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane, smem_u32(stage_buf + warp * (32 * 32)));
+            }
+            tc_fence_before();
+            asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(lempty) : "memory");
+            if (dbg && threadIdx.x == 0 && it < 16) p.dbg[72 + it] = clock64();
+        }
+        if ((MODE == 3 || MODE == 4) && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    // neither CTA may exit (or free its TMEM) while the pair's MMAs / remote arrives can still touch it
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (warp == ALLOC_WARP) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN_)) : "memory");
 }
 
 // fp32 [M,K] -> bf16 (hi | lo) [M, 2*Kp], zero padded to Kp
@@ -844,6 +1123,15 @@ bool make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, i
 }  // namespace
 
 static long long* g_tc_dbg = nullptr;
+static int g_tc_bn = 0;        // tuning hook (tools/tc_tile_sweep.py): force the tile width (128 / 256), 0 = automatic
+static int g_tc_cluster = -1;  // tuning hook: force the 2-CTA multicast kernel on (1) / off (0), -1 = AMB200_TC_CLUSTER / default
+static int g_tc_bk = 0;        // tuning hook: 32 forces the 64-byte-row K block in the CTA-pair kernel
+extern "C" void am_tc_set_bk_(int bk) { g_tc_bk = bk; }
+static int g_tc_2sm = -1;      // tuning hook: CTA-pair (cta_group::2) kernel on (1) / off (0), -1 = AMB200_TC_2SM / default (on)
+extern "C" void am_tc_set_2sm_(int on) { g_tc_2sm = on; }
+static int g_tc_lsu = -1;      // tuning hook: 1 = LSU epilogues (MODE 1 / 2) instead of the TMA ones (MODE 3 / 4), -1 = AMB200_TC_EPI / default
+extern "C" void am_tc_set_tile_(int bn, int cluster) { g_tc_bn = bn; g_tc_cluster = cluster; }
+extern "C" void am_tc_set_epi_(int lsu) { g_tc_lsu = lsu; }
 // debug hook (not part of the public header): timeline buffer of >= 200 int64 for the next am_linear_tc launches
 extern "C" void am_tc_set_debug_(void* buf) { g_tc_dbg = reinterpret_cast<long long*>(buf); }
 
@@ -880,7 +1168,7 @@ extern "C" int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp
     if (variant == 3) {
         // tile width: 256 when that still gives every SM >= ~2 tiles, else 128 (more, smaller tiles)
         const int mt = cdiv(M, BM);
-        const bool wide = N >= 256 && (int64_t)mt * cdiv(N, 256) >= 2 * AM_NUM_SMS;
+        const bool wide = g_tc_bn ? (g_tc_bn == 256 && N >= 256) : (N >= 256 && (int64_t)mt * cdiv(N, 256) >= 2 * AM_NUM_SMS);
         const int bn = wide ? 256 : 128;
         const int nt = cdiv(N, bn), total = mt * nt;
         CUtensorMap tmA, tmB;
@@ -894,10 +1182,44 @@ extern "C" int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp
         static int cl_env = -1;
         if (cl_env < 0) { const char* e = getenv("AMB200_TC_CLUSTER"); cl_env = (e && !strcmp(e, "0")) ? 0 : 1; }
         const int pairs = cdiv(mt, 2) * nt;
-        const bool use_cluster = cl_env && pairs >= 16;
+        static int sm2_env = -1;
+        if (sm2_env < 0) { const char* e = getenv("AMB200_TC_2SM"); sm2_env = (e && !strcmp(e, "0")) ? 0 : 1; }
+        const bool use_2sm = (g_tc_2sm >= 0 ? g_tc_2sm : sm2_env) && pairs >= 16;
+        const bool use_cluster = !use_2sm && (g_tc_cluster >= 0 ? g_tc_cluster : cl_env) && pairs >= 16;
         const int grid_cl = 2 * (pairs < AM_NUM_SMS / 2 ? pairs : AM_NUM_SMS / 2);
         CUtensorMap tmBh = tmB;
-        if (use_cluster) AM_REQUIRE(make_map(&tmBh, W2, (uint64_t)N, (uint64_t)2 * Kp, 32, bn / 2), AM_ELAUNCH, "am_linear_tc: cuTensorMapEncodeTiled(W half) failed");
+        // CTA-pair kernel K block: 64 (128-byte smem rows, SWIZZLE_128B) when Kp allows, else 32 (SWIZZLE_64B)
+        const int bk2 = (use_2sm && Kp % 64 == 0 && g_tc_bk != 32) ? 64 : 32;
+        CUtensorMap tmA64 = tmA, tmBh64 = tmB;
+        if (bk2 == 64) {
+            AM_REQUIRE(make_map(&tmA64, A2, (uint64_t)M, (uint64_t)2 * Kp, 64, BM), AM_ELAUNCH, "am_linear_tc: cuTensorMapEncodeTiled(A, BK=64) failed");
+            AM_REQUIRE(make_map(&tmBh64, W2, (uint64_t)N, (uint64_t)2 * Kp, 64, bn / 2), AM_ELAUNCH, "am_linear_tc: cuTensorMapEncodeTiled(W half, BK=64) failed");
+        }
+        if (use_cluster || use_2sm) AM_REQUIRE(make_map(&tmBh, W2, (uint64_t)N, (uint64_t)2 * Kp, 32, bn / 2), AM_ELAUNCH, "am_linear_tc: cuTensorMapEncodeTiled(W half) failed");
+#define AM_TC2_LAUNCH(BN_, NST2_, ACT_, MODE_, BK_)                                                                             \
+    do {                                                                                                                        \
+        constexpr int smem2_ = NST2_ * (2 * BM * BK_ * 2 + BN_ * BK_ * 2) + 1024 + 1024 + 8 * 32 * 32 * 4;                       \
+        static bool attr3_ = false;                                                                                             \
+        if (!attr3_) {                                                                                                          \
+            if (cudaFuncSetAttribute(gemm_tc_2sm_kernel<BN_, NST2_, ACT_, MODE_, BK_>,                                          \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem2_) != cudaSuccess) {                     \
+                am_set_error_("am_linear_tc: shared memory opt-in failed");                                                     \
+                return AM_ELAUNCH;                                                                                              \
+            }                                                                                                                   \
+            attr3_ = true;                                                                                                      \
+        }                                                                                                                       \
+        cudaLaunchConfig_t cfg_ = {};                                                                                           \
+        cfg_.gridDim = dim3(grid_cl); cfg_.blockDim = dim3(TCP_THREADS); cfg_.dynamicSmemBytes = smem2_; cfg_.stream = st;      \
+        cudaLaunchAttribute at_[1];                                                                                             \
+        at_[0].id = cudaLaunchAttributeClusterDimension;                                                                        \
+        at_[0].val.clusterDim.x = 2; at_[0].val.clusterDim.y = 1; at_[0].val.clusterDim.z = 1;                                  \
+        cfg_.attrs = at_; cfg_.numAttrs = 1;                                                                                    \
+        if (cudaLaunchKernelEx(&cfg_, gemm_tc_2sm_kernel<BN_, NST2_, ACT_, MODE_, BK_>, (bk2 == 64 ? tmA64 : tmA),              \
+                               (bk2 == 64 ? tmBh64 : tmBh), tmY, tmR, p, nt, pairs) != cudaSuccess) {                           \
+            am_set_error_("am_linear_tc: CTA-pair launch failed");                                                              \
+            return AM_ELAUNCH;                                                                                                  \
+        }                                                                                                                       \
+    } while (0)
 #define AM_TCP_LAUNCH(BN_, NST_, ACT_, MODE_)                                                                                   \
     do {                                                                                                                        \
         constexpr int smem_ = NST_ * (2 * BM * 32 * 2 + 2 * BN_ * 32 * 2) + 1024 + 1024 + 8 * 32 * 32 * 4;                       \
@@ -910,7 +1232,11 @@ extern "C" int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp
             }                                                                                                                   \
             attr_ = true;                                                                                                       \
         }                                                                                                                       \
-        if (use_cluster) {                                                                                                      \
+        if (use_2sm && bk2 == 64) {                                                                                             \
+            AM_TC2_LAUNCH(BN_, (BN_ == 256 ? 3 : 4), ACT_, MODE_, 64);                                                          \
+        } else if (use_2sm) {                                                                                                   \
+            AM_TC2_LAUNCH(BN_, (BN_ == 256 ? 6 : 8), ACT_, MODE_, 32);                                                          \
+        } else if (use_cluster) {                                                                                               \
             static bool attr2_ = false;                                                                                         \
             if (!attr2_) {                                                                                                      \
                 if (cudaFuncSetAttribute(gemm_tc_cluster_kernel<BN_, NST_, ACT_, MODE_>,                                        \
@@ -926,12 +1252,12 @@ extern "C" int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp
             at_[0].id = cudaLaunchAttributeClusterDimension;                                                                    \
             at_[0].val.clusterDim.x = 2; at_[0].val.clusterDim.y = 1; at_[0].val.clusterDim.z = 1;                              \
             cfg_.attrs = at_; cfg_.numAttrs = 1;                                                                                \
-            if (cudaLaunchKernelEx(&cfg_, gemm_tc_cluster_kernel<BN_, NST_, ACT_, MODE_>, tmA, tmBh, tmY, p, nt, pairs) != cudaSuccess) { \
+            if (cudaLaunchKernelEx(&cfg_, gemm_tc_cluster_kernel<BN_, NST_, ACT_, MODE_>, tmA, tmBh, tmY, tmR, p, nt, pairs) != cudaSuccess) { \
                 am_set_error_("am_linear_tc: cluster launch failed");                                                           \
                 return AM_ELAUNCH;                                                                                              \
             }                                                                                                                   \
         } else                                                                                                                  \
-        gemm_tc_persistent_kernel<BN_, NST_, ACT_, MODE_><<<grid, TCP_THREADS, smem_, st>>>(tmA, tmB, tmY, p, nt, total);              \
+        gemm_tc_persistent_kernel<BN_, NST_, ACT_, MODE_><<<grid, TCP_THREADS, smem_, st>>>(tmA, tmB, tmY, tmR, p, nt, total);         \
     } while (0)
         // epilogue mode: 1 / 2 = specialised fast paths of the big trunk GEMMs, 0 = general
         const int a15 = act & 15;
@@ -942,7 +1268,8 @@ extern "C" int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp
         if (plain && Y2 && !Y && !residual && Np2 == N && (N % 4) == 0 && (a15 == AM_ACT_NONE || a15 == AM_ACT_GELU)) mode = 1;
         static int lsu_epi = -1;
         if (lsu_epi < 0) { const char* e = getenv("AMB200_TC_EPI"); lsu_epi = (e && !strcmp(e, "lsu")) ? 1 : 0; }
-        if (mode == 1 && !lsu_epi && (N % 32) == 0) {
+        const bool lsu = g_tc_lsu >= 0 ? g_tc_lsu != 0 : lsu_epi != 0;
+        if (mode == 1 && !lsu && (N % 32) == 0) {
             // output tensor map: Y2 [M, 2*Np2] bf16, box 32 cols x 32 rows, SWIZZLE_64B
             EncodeTiledFn enc = get_encode();
             cuuint64_t gdim[2] = {(cuuint64_t)2 * Np2, (cuuint64_t)M};
@@ -954,11 +1281,27 @@ extern "C" int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp
         }
         if (plain && Y && !Y2 && (a15 == AM_ACT_NONE || a15 == AM_ACT_GELU) && (ldy % 4) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15u) == 0 &&
             (!residual || ((ldr % 4) == 0 && (reinterpret_cast<uintptr_t>(residual) & 15u) == 0))) mode = 2;
+        CUtensorMap tmR = tmA;  // placeholder unless MODE 4 reads a residual
+        if (mode == 2 && !lsu) {
+            // fp32 tensor maps: Y [M, ldy] and residual [M, ldr], box 16 cols x 32 rows (64-byte rows), SWIZZLE_64B
+            EncodeTiledFn enc = get_encode();
+            auto f32map = [&](CUtensorMap* mp, const float* ptr, int ld) {
+                cuuint64_t gdim[2] = {(cuuint64_t)N, (cuuint64_t)M};
+                cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+                cuuint32_t box[2] = {16, 32};
+                cuuint32_t estr[2] = {1, 1};
+                return enc && enc(mp, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            };
+            if (f32map(&tmY, Y, ldy) && (!residual || f32map(&tmR, residual, ldr))) mode = 4;
+        }
 #define AM_TCP_BY_MODE(BN_, NST_)                                                                  \
     if (mode == 3 && a15 == AM_ACT_GELU) AM_TCP_LAUNCH(BN_, NST_, AM_ACT_GELU, 3);                  \
     else if (mode == 3) AM_TCP_LAUNCH(BN_, NST_, AM_ACT_NONE, 3);                                   \
     else if (mode == 1 && a15 == AM_ACT_GELU) AM_TCP_LAUNCH(BN_, NST_, AM_ACT_GELU, 1);             \
     else if (mode == 1) AM_TCP_LAUNCH(BN_, NST_, AM_ACT_NONE, 1);                                   \
+    else if (mode == 4 && a15 == AM_ACT_GELU) AM_TCP_LAUNCH(BN_, NST_, AM_ACT_GELU, 4);             \
+    else if (mode == 4) AM_TCP_LAUNCH(BN_, NST_, AM_ACT_NONE, 4);                                   \
     else if (mode == 2 && a15 == AM_ACT_GELU) AM_TCP_LAUNCH(BN_, NST_, AM_ACT_GELU, 2);             \
     else if (mode == 2) AM_TCP_LAUNCH(BN_, NST_, AM_ACT_NONE, 2);                                   \
     else switch (a15) {                                                                            \
@@ -970,6 +1313,7 @@ extern "C" int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp
         if (wide) { AM_TCP_BY_MODE(256, 4) } else { AM_TCP_BY_MODE(128, 6) }
 #undef AM_TCP_BY_MODE
 #undef AM_TCP_LAUNCH
+#undef AM_TC2_LAUNCH
         AM_LAUNCH_CHECK("linear_tc");
         return AM_OK;
     }

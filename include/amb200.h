@@ -268,9 +268,10 @@ int am_masked_mse_bwd(const float* x0, const float* pred, const uint8_t* mask, c
  * Fused flat-buffer AdamW == torch.optim.AdamW(lr, betas, eps, weight_decay) applied to every parameter in ONE launch:
  *   g' = g*grad_scale;  p *= 1 - lr*wd;  m = b1*m + (1-b1)*g';  v = b2*v + (1-b2)*g'^2;
  *   p -= lr/(1-b1^step) * m / (sqrt(v)/sqrt(1-b2^step) + eps);   step >= 1 is the 1-based update count.
+ * Hyper-parameters are doubles (1-beta and the bias corrections are formed in double and rounded once, as torch does).
  * zero_grad != 0 also clears g (the next step's optimizer.zero_grad()).  All four buffers: fp32, n elements, 16-byte aligned. */
-int am_adamw_flat(float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
-                  float weight_decay, int64_t step, float grad_scale, int zero_grad, am_stream_t stream);
+int am_adamw_flat(float* p, float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2, double eps,
+                  double weight_decay, int64_t step, float grad_scale, int zero_grad, am_stream_t stream);
 
 #ifdef __cplusplus
 }

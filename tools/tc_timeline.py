@@ -5,7 +5,8 @@ sys.path.insert(0, os.path.join(ROOT, "afford-motion_b200"))
 import torch
 from amb200 import ops, lib
 dev = "cuda:0"
-M, N, K = 32 * 326, 1536, 512
+M = 32 * 326
+N, K = int(os.environ.get("TC_N", "1536")), int(os.environ.get("TC_K", "512"))
 g = torch.Generator(device=dev).manual_seed(0)
 x, w = torch.randn(M, K, device=dev, generator=g), torch.randn(N, K, device=dev, generator=g) / 22
 xs, wsp = ops.split_bf16(x, M, K), ops.split_bf16(w, N, K)
@@ -34,9 +35,9 @@ L.am_tc_set_debug_(None)
 d = dbg.cpu().tolist()
 t0 = d[0]
 if os.environ.get("AMB200_TC_VARIANT", "persistent") == "persistent":
-    print("tile  mma_committed  epi_start  epi_end   (cycles since CTA 0 start)")
+    print("tile  mma_committed  epi_start  epi_end   (cycles since CTA 0 start; the CTA-pair kernel records commit and epi_end only)")
     for it in range(6):
-        print(it, d[8 + it] - t0, d[40 + it] - t0, d[72 + it] - t0)
+        print(it, *[(d[o + it] - t0 if d[o + it] else None) for o in (8, 40, 72)])
     sys.exit(0)
 nkb = K // (64 if os.environ.get("AMB200_TC_VARIANT") == "64x3" else 32)
 print("prologue sync done +", d[1] - t0, " tmem_full seen +", d[2] - t0, " epilogue done +", d[3] - t0, " teardown +", d[4] - t0)
