@@ -18,6 +18,8 @@ constexpr int MAXJ = 11;     // ceil(352/32)
 __global__ void __launch_bounds__(ATT_WARPS * 32, 1)
 mha_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out, const uint8_t* __restrict__ key_pad, int S, int H, float scale,
                __nv_bfloat16* __restrict__ out2) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ __align__(16) float smem[];
     const int SP = ((S + 31) / 32) * 32 + 1;
     float* Kt = smem;                         // [HD][SP]
@@ -154,7 +156,7 @@ extern "C" int am_mha_fwd(const float* qkv, float* out, const uint8_t* key_pad, 
     }
     AM_REQUIRE(smem <= 227 * 1024, AM_EINVAL, "am_mha_fwd: sequence too long for the shared-memory staging");
     dim3 grid(cdiv(S, QTILE), H, B);
-    mha_fwd_kernel<<<grid, ATT_WARPS * 32, smem, as_stream(stream)>>>(qkv, out, key_pad, S, H, scale, reinterpret_cast<__nv_bfloat16*>(out2));
+    am_launch(mha_fwd_kernel, dim3(grid), dim3(ATT_WARPS * 32), smem, as_stream(stream), 1, qkv, out, key_pad, S, H, scale, reinterpret_cast<__nv_bfloat16*>(out2));
     AM_LAUNCH_CHECK("mha_fwd");
     return AM_OK;
 }

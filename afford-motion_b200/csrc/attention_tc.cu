@@ -143,6 +143,7 @@ constexpr uint32_t IDESC_PV = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) /*
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 mha_tc_kernel(const __grid_constant__ CUtensorMap tm, AttParams p) {
+    pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -178,6 +179,7 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tm, AttParams p) {
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (warp == 9 && lane < 12) {  // attendable-key bitmasks (key < S and not padded)
+        pdl_wait();  // key_pad may have been written by the kernel just before this one
         uint32_t bits = 0;
         for (int k = 0; k < 32; ++k) {
             int key = lane * 32 + k;
@@ -190,6 +192,7 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tm, AttParams p) {
     __syncthreads();
     fence_after_a();
     const uint32_t tmem_base = *tmem_holder;
+    pdl_wait();  // barrier init / TMEM allocation above overlapped the in_proj GEMM's tail
     if (p.dbg && blockIdx.x == 0 && threadIdx.x == 320) p.dbg[0] = clock64();
 
     if (warp == 10) {
@@ -420,7 +423,7 @@ extern "C" int am_mha_tc_fwd(const void* qkv2, float* out, void* out2, const uin
         attr = true;
     }
     AttParams p{B, S, H, scale, key_pad, out, reinterpret_cast<__nv_bfloat16*>(out2), g_att_dbg};
-    mha_tc_kernel<<<B * H, ATT_THREADS, ATT_SMEM, as_stream(stream)>>>(tm, p);
+    am_launch(mha_tc_kernel, dim3(B * H), dim3(ATT_THREADS), ATT_SMEM, as_stream(stream), 1, tm, p);
     AM_LAUNCH_CHECK("mha_tc_fwd");
     return AM_OK;
 }

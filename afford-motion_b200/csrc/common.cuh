@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include "../../include/amb200.h"
 
 extern "C" void am_set_error_(const char* msg);
@@ -27,6 +28,39 @@ extern "C" void am_count_launch_(int n);
     } while (0)
 
 static inline cudaStream_t as_stream(am_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---- Programmatic dependent launch (PDL).  One denoise step is a chain of ~45 dependent kernels; measured on B200 the gap
+// between two of them (grid drain + launch latency + the next kernel's prologue) is ~4.7 us per tcgen05 GEMM.  Kernels launched
+// through am_launch() may START while their predecessor in the stream is still running: they execute their prologue
+// (barrier init, TMEM allocation, tensor-map prefetch) and then block in pdl_wait() until the predecessor has completed and
+// its memory is visible.  RULE: a kernel launched through am_launch() must call pdl_wait() before its first access to global
+// memory another kernel may have written (or may still read).  AMB200_PDL=0 launches everything fully serialised.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+static inline bool am_pdl_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("AMB200_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on != 0;
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t am_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    int n = 0;
+    if (am_pdl_enabled()) {
+        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (cluster_x > 1) {
+        at[n].id = cudaLaunchAttributeClusterDimension;
+        at[n].val.clusterDim.x = (unsigned)cluster_x; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    cfg.attrs = at; cfg.numAttrs = (unsigned)n;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 #define AM_NUM_SMS 148
 

@@ -52,6 +52,8 @@ __global__ void sampler_update_kernel(const float* __restrict__ x0_hat, const fl
                                       const float* __restrict__ c2, const float* __restrict__ c3, float eta,
                                       const int32_t* __restrict__ t, int t_stride, int B, int64_t per_sample, uint64_t seed,
                                       const uint64_t* __restrict__ seed_dev, int64_t sample0, int vec_ok) {
+    pdl_launch_dependents();
+    pdl_wait();
     if (seed_dev) seed = *seed_dev;
     int64_t nblk = (per_sample + 3) / 4;
     int64_t total = nblk * B;
@@ -128,12 +130,16 @@ __global__ void masked_mse_kernel(const float* __restrict__ x0, const float* __r
 }
 
 __global__ void add_i32_kernel(int32_t* dst, int32_t delta, int n) {
+    pdl_launch_dependents();
+    pdl_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] += delta;
 }
 
 __global__ void gather_time_token_kernel(float* __restrict__ X, int S, int D, int row, const float* __restrict__ table,
                                          const int32_t* __restrict__ t, int t_stride, __nv_bfloat16* __restrict__ X2) {
+    pdl_launch_dependents();
+    pdl_wait();
     int b = blockIdx.x;
     int tb = t[b * t_stride];
     const float* src = table + (int64_t)tb * D;
@@ -181,7 +187,7 @@ extern "C" int am_p_sample_update(const float* x0_hat, const float* x_t, float* 
     AM_REQUIRE(B > 0 && per_sample > 0 && (t_stride == 0 || t_stride == 1), AM_EINVAL, "am_p_sample_update: bad dims");
     int vec_ok = (per_sample % 4 == 0) && aligned16(x0_hat) && aligned16(x_t) && aligned16(x_prev) && (!noise || aligned16(noise));
     int64_t items = ((per_sample + 3) / 4) * B;
-    sampler_update_kernel<0><<<ew_grid(items), EW_THREADS, 0, as_stream(stream)>>>(x0_hat, x_t, x_prev, noise, coef1, coef2, logvar, nullptr,
+    am_launch(sampler_update_kernel<0>, dim3(ew_grid(items)), dim3(EW_THREADS), 0, as_stream(stream), 1, x0_hat, x_t, x_prev, noise, coef1, coef2, logvar, nullptr,
                                                                                    0.f, t, t_stride, B, per_sample, seed, seed_dev, sample0, vec_ok);
     AM_LAUNCH_CHECK("p_sample_update");
     return AM_OK;
@@ -194,7 +200,7 @@ extern "C" int am_ddim_update(const float* x0_hat, const float* x_t, float* x_pr
     AM_REQUIRE(B > 0 && per_sample > 0 && (t_stride == 0 || t_stride == 1), AM_EINVAL, "am_ddim_update: bad dims");
     int vec_ok = (per_sample % 4 == 0) && aligned16(x0_hat) && aligned16(x_t) && aligned16(x_prev) && (!noise || aligned16(noise));
     int64_t items = ((per_sample + 3) / 4) * B;
-    sampler_update_kernel<1><<<ew_grid(items), EW_THREADS, 0, as_stream(stream)>>>(x0_hat, x_t, x_prev, noise, sqrt_recip_ac, sqrt_recipm1_ac,
+    am_launch(sampler_update_kernel<1>, dim3(ew_grid(items)), dim3(EW_THREADS), 0, as_stream(stream), 1, x0_hat, x_t, x_prev, noise, sqrt_recip_ac, sqrt_recipm1_ac,
                                                                                    ac, ac_prev, eta, t, t_stride, B, per_sample, seed, seed_dev, sample0, vec_ok);
     AM_LAUNCH_CHECK("ddim_update");
     return AM_OK;
@@ -217,7 +223,7 @@ extern "C" int am_masked_mse(const float* x0, const float* pred, const uint8_t* 
 
 extern "C" int am_add_i32(int32_t* dst, int32_t delta, int n, am_stream_t stream) {
     AM_REQUIRE(dst && n > 0, AM_EINVAL, "am_add_i32: bad args");
-    add_i32_kernel<<<cdiv(n, 64), 64, 0, as_stream(stream)>>>(dst, delta, n);
+    am_launch(add_i32_kernel, dim3(cdiv(n, 64)), dim3(64), 0, as_stream(stream), 1, dst, delta, n);
     AM_LAUNCH_CHECK("add_i32");
     return AM_OK;
 }
@@ -225,7 +231,7 @@ extern "C" int am_add_i32(int32_t* dst, int32_t delta, int n, am_stream_t stream
 extern "C" int am_gather_time_token(float* X, int S, int D, int row, const float* table, const int32_t* t, int t_stride, int B,
                                     void* X2, am_stream_t stream) {
     AM_REQUIRE(X && table && t && B > 0 && S > 0 && D > 0 && row >= 0 && row < S, AM_EINVAL, "am_gather_time_token: bad args");
-    gather_time_token_kernel<<<B, 128, 0, as_stream(stream)>>>(X, S, D, row, table, t, t_stride, reinterpret_cast<__nv_bfloat16*>(X2));
+    am_launch(gather_time_token_kernel, dim3(B), dim3(128), 0, as_stream(stream), 1, X, S, D, row, table, t, t_stride, reinterpret_cast<__nv_bfloat16*>(X2));
     AM_LAUNCH_CHECK("gather_time_token");
     return AM_OK;
 }

@@ -22,6 +22,8 @@ __device__ __forceinline__ int64_t map_row(int m, int gin, int gout, int off) {
 
 template <int BM, int BN>
 __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int BK = 16;
     constexpr int TM = BM / 16, TN = BN / 16;  // 8x8 (128 tile) or 4x4 (64 tile)
     constexpr int HM = TM / 2 > 4 ? 4 : (TM >= 4 ? 4 : TM), HN = TN >= 4 ? 4 : TN;
@@ -190,10 +192,10 @@ extern "C" int am_linear_f32(const float* X, int ldx, const float* W, int ldw, f
     int64_t tiles128 = (int64_t)cdiv(M, 128) * cdiv(N, 128);
     if (tiles128 >= AM_NUM_SMS) {
         dim3 grid(cdiv(N, 128), cdiv(M, 128));
-        gemm_f32_kernel<128, 128><<<grid, 256, 0, as_stream(stream)>>>(p);
+        am_launch(gemm_f32_kernel<128, 128>, dim3(grid), dim3(256), 0, as_stream(stream), 1, p);
     } else {
         dim3 grid(cdiv(N, 64), cdiv(M, 64));
-        gemm_f32_kernel<64, 64><<<grid, 256, 0, as_stream(stream)>>>(p);
+        am_launch(gemm_f32_kernel<64, 64>, dim3(grid), dim3(256), 0, as_stream(stream), 1, p);
     }
     AM_LAUNCH_CHECK("linear_f32");
     return AM_OK;

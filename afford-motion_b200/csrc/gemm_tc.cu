@@ -660,6 +660,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     constexpr int B_SUB = BN_ * BK * 2;         // 8 / 16 KB
     constexpr int STAGE_BYTES = 2 * A_SUB + 2 * B_SUB;
     constexpr uint32_t IDESC_P = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN_ >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + NST * STAGE_BYTES);
@@ -694,6 +695,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    pdl_wait();  // prologue above overlapped the previous kernel; from here on its results are complete and visible
     if (dbg && threadIdx.x == 0) p.dbg[0] = clock64();
 
     if (warp == PRODUCER_WARP) {
@@ -793,6 +795,7 @@ gemm_tc_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     constexpr int B_SUB = BN_ * BK * 2;         // 8 / 16 KB
     constexpr int STAGE_BYTES = 2 * A_SUB + 2 * B_SUB;
     constexpr uint32_t IDESC_P = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN_ >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + NST * STAGE_BYTES);
@@ -833,6 +836,7 @@ gemm_tc_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    pdl_wait();  // prologue above overlapped the previous kernel; from here on its results are complete and visible
     if (dbg && threadIdx.x == 0) p.dbg[0] = clock64();
 
     if (warp == PRODUCER_WARP) {
@@ -937,13 +941,26 @@ gemm_tc_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 template <int BN_, int NST, int ACT, int MODE, int BK>
 __global__ void __launch_bounds__(TCP_THREADS, 1)
 gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR, TcParams p, int n_tiles,
-                   int total_pairs) {
+                   const __grid_constant__ CUtensorMap tmBq, const __grid_constant__ CUtensorMap tmY,
+                   const __grid_constant__ CUtensorMap tmR, TcParams p, int n_tiles, int wide_items, int total_items) {
+    // Work items: [0, wide_items) are 256 x BN_ pair tiles (m-pair = idx / n_tiles, n-tile = idx % n_tiles); items beyond are the
+    // REMAINING pair tiles cut into two BN_/2-wide halves each.  M*N / (148 SMs x tile) is rarely an integer (2.2 for the
+    // N = 512 / 1024 trunk GEMMs): instead of a third full round on a fifth of the SMs, the last partial round runs as
+    // half-width tiles spread over twice as many CTA pairs (tmBq: W box of BN_/4 rows per CTA).
+    auto decode = [&](int idx, int& mp, int& n0, bool& narrow) {
+        if (idx < wide_items) { mp = idx / n_tiles; n0 = (idx % n_tiles) * BN_; narrow = false; }
+        else {
+            const int u = idx - wide_items, w = wide_items + (u >> 1);
+            mp = w / n_tiles; n0 = (w % n_tiles) * BN_ + (u & 1) * (BN_ / 2); narrow = true;
+        }
+    };
+    constexpr uint32_t IDESC_N = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((BN_ / 2) >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
     // BK = 32: 64-byte operand rows (SWIZZLE_64B); BK = 64: 128-byte rows (SWIZZLE_128B)
     constexpr int A_SUB = BM * BK * 2;            // this CTA's 128 rows of A (hi or lo)
     constexpr int B_SUB = (BN_ / 2) * BK * 2;     // this CTA's half of the W tile (hi or lo)
     constexpr int STAGE_BYTES = 2 * A_SUB + 2 * B_SUB;
     constexpr uint32_t IDESC_P = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN_ >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+    pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + NST * STAGE_BYTES);
@@ -981,30 +998,40 @@ gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    pdl_wait();  // prologue above overlapped the previous kernel; from here on its results are complete and visible
     const bool dbg = p.dbg && blockIdx.x == 0;
-    if (dbg && threadIdx.x == 0) p.dbg[0] = clock64();
+    if (dbg && threadIdx.x == 0) {
+        p.dbg[0] = clock64();
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+        p.dbg[1] = (long long)ns;
+    }
 
     if (warp == PRODUCER_WARP) {
         // ===================== TMA producer (both CTAs) =====================
         if (lane == 0) {
             uint32_t kbc = 0;
-            for (int tile = cluster_id; tile < total_pairs; tile += num_clusters) {
-                const int m0 = ((tile / n_tiles) * 2 + (int)cta_rank) * BM;
-                const int nh = (tile % n_tiles) * BN_ + (int)cta_rank * (BN_ / 2);
+            for (int tile = cluster_id; tile < total_items; tile += num_clusters) {
+                int mp, n0; bool narrow;
+                decode(tile, mp, n0, narrow);
+                const int m0 = (mp * 2 + (int)cta_rank) * BM;
+                const int nh = n0 + (int)cta_rank * (narrow ? BN_ / 4 : BN_ / 2);
+                const CUtensorMap* tmW = narrow ? &tmBq : &tmB;
+                const uint32_t stage_tx = (uint32_t)(2 * A_SUB + (narrow ? B_SUB : 2 * B_SUB));
                 for (int kb = 0; kb < nkb; ++kb, ++kbc) {
                     const int s = kbc % NST;
                     mbar_wait(&empty[s], ((kbc / NST) & 1) ^ 1);   // released in both CTAs by the leader's commit multicast
                     const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
                     uint32_t lbar;  // the LEADER's full[s] in the cluster shared window
                     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(lbar) : "r"(smem_u32(&full[s])), "r"(0u));
-                    if (leader) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full[s])), "r"((uint32_t)(2 * STAGE_BYTES)) : "memory");
+                    if (leader) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full[s])), "r"(2u * stage_tx) : "memory");
 #define AM_TMA_2SM(dst_, map_, c0_, c1_)                                                                                              \
     asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" \
                  ::"r"(dst_), "l"(reinterpret_cast<uint64_t>(map_)), "r"(lbar), "r"(c0_), "r"(c1_) : "memory")
                     AM_TMA_2SM(st, &tmA, kb * BK, m0);                               // A_hi (own 128 rows)
                     AM_TMA_2SM(st + A_SUB, &tmA, p.Kp + kb * BK, m0);                // A_lo
-                    AM_TMA_2SM(st + 2 * A_SUB, &tmB, kb * BK, nh);                   // W_hi, own half of the n-tile
-                    AM_TMA_2SM(st + 2 * A_SUB + B_SUB, &tmB, p.Kp + kb * BK, nh);    // W_lo
+                    AM_TMA_2SM(st + 2 * A_SUB, tmW, kb * BK, nh);                    // W_hi, own half of the n-tile
+                    AM_TMA_2SM(st + 2 * A_SUB + B_SUB, tmW, p.Kp + kb * BK, nh);     // W_lo
 #undef AM_TMA_2SM
                 }
             }
@@ -1014,8 +1041,9 @@ gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (lane == 0 && leader) {
             uint32_t kbc = 0;
             int it = 0;
-            for (int tile = cluster_id; tile < total_pairs; tile += num_clusters, ++it) {
+            for (int tile = cluster_id; tile < total_items; tile += num_clusters, ++it) {
                 const int ab = it & 1;
+                const uint32_t idesc = tile < wide_items ? IDESC_P : IDESC_N;
                 mbar_wait(&tmem_empty[ab], (((it >> 1) & 1) ^ 1));
                 tc_fence_after();
                 const uint32_t d = tmem_base + (uint32_t)(ab * BN_);
@@ -1031,7 +1059,7 @@ gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         const uint64_t ko = (uint64_t)(k * 2);
 #define AM_UMMA_2SM(a_, b_, acc_)                                                                                     \
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" \
-                 ::"r"(d), "l"(a_), "l"(b_), "r"(IDESC_P), "r"((uint32_t)(acc_)) : "memory")
+                 ::"r"(d), "l"(a_), "l"(b_), "r"(idesc), "r"((uint32_t)(acc_)) : "memory")
                         AM_UMMA_2SM(a_lo + ko, w_hi + ko, (kb | k) ? 1u : 0u);
                         AM_UMMA_2SM(a_hi + ko, w_lo + ko, 1u);
                         AM_UMMA_2SM(a_hi + ko, w_hi + ko, 1u);
@@ -1050,25 +1078,38 @@ gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int q = warp & 3, half = warp >> 2;
         int it = 0;
         uint32_t epi_phases = 0;
-        for (int tile = cluster_id; tile < total_pairs; tile += num_clusters, ++it) {
+        for (int tile = cluster_id; tile < total_items; tile += num_clusters, ++it) {
             const int ab = it & 1;
-            const int m0 = ((tile / n_tiles) * 2 + (int)cta_rank) * BM, n0 = (tile % n_tiles) * BN_;
+            int mp, n0; bool narrow;
+            decode(tile, mp, n0, narrow);
+            const int m0 = (mp * 2 + (int)cta_rank) * BM;
             uint32_t lempty;  // the leader's tmem_empty[ab]
             asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(lempty) : "r"(smem_u32(&tmem_empty[ab])), "r"(0u));
             if (MODE == 4) {
-                epilogue_tile_tma_f32<ACT, BN_>(p, &tmY, &tmR, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane,
-                                                smem_u32(stage_buf + warp * (32 * 32)), smem_u32(epi_bars + warp * 2), epi_phases,
-                                                &tmem_full[ab], (uint32_t)((it >> 1) & 1));
+                if (narrow)
+                    epilogue_tile_tma_f32<ACT, BN_ / 2>(p, &tmY, &tmR, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane,
+                                                        smem_u32(stage_buf + warp * (32 * 32)), smem_u32(epi_bars + warp * 2), epi_phases,
+                                                        &tmem_full[ab], (uint32_t)((it >> 1) & 1));
+                else
+                    epilogue_tile_tma_f32<ACT, BN_>(p, &tmY, &tmR, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane,
+                                                    smem_u32(stage_buf + warp * (32 * 32)), smem_u32(epi_bars + warp * 2), epi_phases,
+                                                    &tmem_full[ab], (uint32_t)((it >> 1) & 1));
             } else {
                 mbar_wait(&tmem_full[ab], (it >> 1) & 1);
                 tc_fence_after();
-                if (MODE == 3) epilogue_tile_tma<ACT, BN_>(p, &tmY, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane, smem_u32(stage_buf + warp * (32 * 32)));
+                if (MODE == 3 && narrow) epilogue_tile_tma<ACT, BN_ / 2>(p, &tmY, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane, smem_u32(stage_buf + warp * (32 * 32)));
+                else if (MODE == 3) epilogue_tile_tma<ACT, BN_>(p, &tmY, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane, smem_u32(stage_buf + warp * (32 * 32)));
                 else if (MODE == 0) epilogue_tile_coalesced<ACT, BN_>(p, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane, stage_buf + warp * (32 * 32));
                 else epilogue_tile_fast<ACT, BN_, MODE>(p, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane, smem_u32(stage_buf + warp * (32 * 32)));
             }
             tc_fence_before();
             asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(lempty) : "memory");
-            if (dbg && threadIdx.x == 0 && it < 16) p.dbg[72 + it] = clock64();
+            if (dbg && threadIdx.x == 0 && it < 16) {
+                p.dbg[72 + it] = clock64();
+                unsigned long long ns;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+                p.dbg[2] = (long long)ns;  // wall clock at the end of the latest epilogue -> actual SM frequency of this launch
+            }
         }
         if ((MODE == 3 || MODE == 4) && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
@@ -1081,6 +1122,8 @@ gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
 // fp32 [M,K] -> bf16 (hi | lo) [M, 2*Kp], zero padded to Kp
 __global__ void split_bf16_kernel(const float* __restrict__ X, int ldx, __nv_bfloat16* __restrict__ X2, int Kp, int M, int K) {
+    pdl_launch_dependents();
+    pdl_wait();
     int64_t total = (int64_t)M * Kp;
     for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
         int m = (int)(g / Kp), k = (int)(g - (int64_t)m * Kp);
@@ -1125,6 +1168,8 @@ bool make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, i
 static long long* g_tc_dbg = nullptr;
 static int g_tc_bn = 0;        // tuning hook (tools/tc_tile_sweep.py): force the tile width (128 / 256), 0 = automatic
 static int g_tc_cluster = -1;  // tuning hook: force the 2-CTA multicast kernel on (1) / off (0), -1 = AMB200_TC_CLUSTER / default
+static int g_tc_mixed = 1;     // tuning hook: 0 disables the half-width tail items of the CTA-pair kernel
+extern "C" void am_tc_set_mixed_(int on) { g_tc_mixed = on; }
 static int g_tc_bk = 0;        // tuning hook: 32 forces the 64-byte-row K block in the CTA-pair kernel
 extern "C" void am_tc_set_bk_(int bk) { g_tc_bk = bk; }
 static int g_tc_2sm = -1;      // tuning hook: CTA-pair (cta_group::2) kernel on (1) / off (0), -1 = AMB200_TC_2SM / default (on)
@@ -1140,7 +1185,7 @@ extern "C" int am_split_bf16(const float* X, int ldx, void* X2, int Kp, int M, i
     int64_t total = (int64_t)M * Kp;
     int64_t blocks = (total + 255) / 256;
     int grid = (int)(blocks < (int64_t)AM_NUM_SMS * 8 ? blocks : (int64_t)AM_NUM_SMS * 8);
-    split_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>(X, ldx, reinterpret_cast<__nv_bfloat16*>(X2), Kp, M, K);
+    am_launch(split_bf16_kernel, dim3(grid), dim3(256), 0, as_stream(stream), 1, X, ldx, reinterpret_cast<__nv_bfloat16*>(X2), Kp, M, K);
     AM_LAUNCH_CHECK("split_bf16");
     return AM_OK;
 }
@@ -1168,7 +1213,16 @@ extern "C" int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp
     if (variant == 3) {
         // tile width: 256 when that still gives every SM >= ~2 tiles, else 128 (more, smaller tiles)
         const int mt = cdiv(M, BM);
-        const bool wide = g_tc_bn ? (g_tc_bn == 256 && N >= 256) : (N >= 256 && (int64_t)mt * cdiv(N, 256) >= 2 * AM_NUM_SMS);
+        static int sm2_env = -1;
+        if (sm2_env < 0) { const char* e = getenv("AMB200_TC_2SM"); sm2_env = (e && !strcmp(e, "0")) ? 0 : 1; }
+        const bool sm2_on = (g_tc_2sm >= 0 ? g_tc_2sm : sm2_env) != 0;
+        // trunk-shaped GEMMs (plain epilogue -> TMA-store modes 3 / 4) run 256-wide on the CTA-pair kernel, whose last partial
+        // round is cut into half-width items; everything else: 256 only when that still gives every SM >= ~2 tiles
+        const bool trunk_like = yin_g == 0 && res_mod == 0 && (N % 256) == 0 && !(act & AM_ACT_AFTER_RES) &&
+                                ((Y2 && !Y && !residual && Np2 == N) || (Y && !Y2));
+        const bool wide = g_tc_bn ? (g_tc_bn == 256 && N >= 256)
+                                  : (N >= 256 && ((int64_t)mt * cdiv(N, 256) >= 2 * AM_NUM_SMS ||
+                                                  (sm2_on && g_tc_mixed && trunk_like && cdiv(mt, 2) * (N / 256) >= 16)));
         const int bn = wide ? 256 : 128;
         const int nt = cdiv(N, bn), total = mt * nt;
         CUtensorMap tmA, tmB;
@@ -1182,9 +1236,7 @@ extern "C" int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp
         static int cl_env = -1;
         if (cl_env < 0) { const char* e = getenv("AMB200_TC_CLUSTER"); cl_env = (e && !strcmp(e, "0")) ? 0 : 1; }
         const int pairs = cdiv(mt, 2) * nt;
-        static int sm2_env = -1;
-        if (sm2_env < 0) { const char* e = getenv("AMB200_TC_2SM"); sm2_env = (e && !strcmp(e, "0")) ? 0 : 1; }
-        const bool use_2sm = (g_tc_2sm >= 0 ? g_tc_2sm : sm2_env) && pairs >= 16;
+        const bool use_2sm = sm2_on && pairs >= 16;
         const bool use_cluster = !use_2sm && (g_tc_cluster >= 0 ? g_tc_cluster : cl_env) && pairs >= 16;
         const int grid_cl = 2 * (pairs < AM_NUM_SMS / 2 ? pairs : AM_NUM_SMS / 2);
         CUtensorMap tmBh = tmB;
@@ -1195,6 +1247,10 @@ extern "C" int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp
             AM_REQUIRE(make_map(&tmA64, A2, (uint64_t)M, (uint64_t)2 * Kp, 64, BM), AM_ELAUNCH, "am_linear_tc: cuTensorMapEncodeTiled(A, BK=64) failed");
             AM_REQUIRE(make_map(&tmBh64, W2, (uint64_t)N, (uint64_t)2 * Kp, 64, bn / 2), AM_ELAUNCH, "am_linear_tc: cuTensorMapEncodeTiled(W half, BK=64) failed");
         }
+        // mixed-width tail (CTA-pair kernel, 256-wide tiles): W quarter-tile map for the half-width items
+        CUtensorMap tmBq = tmB;
+        const bool mixed_ok = use_2sm && bn == 256 && g_tc_mixed != 0;
+        if (mixed_ok) AM_REQUIRE(make_map(&tmBq, W2, (uint64_t)N, (uint64_t)2 * Kp, bk2, bn / 4), AM_ELAUNCH, "am_linear_tc: cuTensorMapEncodeTiled(W quarter) failed");
         if (use_cluster || use_2sm) AM_REQUIRE(make_map(&tmBh, W2, (uint64_t)N, (uint64_t)2 * Kp, 32, bn / 2), AM_ELAUNCH, "am_linear_tc: cuTensorMapEncodeTiled(W half) failed");
 #define AM_TC2_LAUNCH(BN_, NST2_, ACT_, MODE_, BK_)                                                                             \
     do {                                                                                                                        \
@@ -1208,14 +1264,11 @@ extern "C" int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp
             }                                                                                                                   \
             attr3_ = true;                                                                                                      \
         }                                                                                                                       \
-        cudaLaunchConfig_t cfg_ = {};                                                                                           \
-        cfg_.gridDim = dim3(grid_cl); cfg_.blockDim = dim3(TCP_THREADS); cfg_.dynamicSmemBytes = smem2_; cfg_.stream = st;      \
-        cudaLaunchAttribute at_[1];                                                                                             \
-        at_[0].id = cudaLaunchAttributeClusterDimension;                                                                        \
-        at_[0].val.clusterDim.x = 2; at_[0].val.clusterDim.y = 1; at_[0].val.clusterDim.z = 1;                                  \
-        cfg_.attrs = at_; cfg_.numAttrs = 1;                                                                                    \
-        if (cudaLaunchKernelEx(&cfg_, gemm_tc_2sm_kernel<BN_, NST2_, ACT_, MODE_, BK_>, (bk2 == 64 ? tmA64 : tmA),              \
-                               (bk2 == 64 ? tmBh64 : tmBh), tmY, tmR, p, nt, pairs) != cudaSuccess) {                           \
+        const bool mixed_ = mixed_ok && BN_ == 256 && (MODE_ == 3 || MODE_ == 4);                                               \
+        const int wide_ = mixed_ ? (pairs / (grid_cl / 2)) * (grid_cl / 2) : pairs;                                              \
+        const int items_ = wide_ + 2 * (pairs - wide_);                                                                         \
+        if (am_launch(gemm_tc_2sm_kernel<BN_, NST2_, ACT_, MODE_, BK_>, dim3(grid_cl), dim3(TCP_THREADS), smem2_, st, 2,       \
+                      (bk2 == 64 ? tmA64 : tmA), (bk2 == 64 ? tmBh64 : tmBh), tmBq, tmY, tmR, p, nt, wide_, items_) != cudaSuccess) { \
             am_set_error_("am_linear_tc: CTA-pair launch failed");                                                              \
             return AM_ELAUNCH;                                                                                                  \
         }                                                                                                                       \
@@ -1246,18 +1299,13 @@ extern "C" int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp
                 }                                                                                                               \
                 attr2_ = true;                                                                                                  \
             }                                                                                                                   \
-            cudaLaunchConfig_t cfg_ = {};                                                                                       \
-            cfg_.gridDim = dim3(grid_cl); cfg_.blockDim = dim3(TCP_THREADS); cfg_.dynamicSmemBytes = smem_; cfg_.stream = st;   \
-            cudaLaunchAttribute at_[1];                                                                                         \
-            at_[0].id = cudaLaunchAttributeClusterDimension;                                                                    \
-            at_[0].val.clusterDim.x = 2; at_[0].val.clusterDim.y = 1; at_[0].val.clusterDim.z = 1;                              \
-            cfg_.attrs = at_; cfg_.numAttrs = 1;                                                                                \
-            if (cudaLaunchKernelEx(&cfg_, gemm_tc_cluster_kernel<BN_, NST_, ACT_, MODE_>, tmA, tmBh, tmY, tmR, p, nt, pairs) != cudaSuccess) { \
+            if (am_launch(gemm_tc_cluster_kernel<BN_, NST_, ACT_, MODE_>, dim3(grid_cl), dim3(TCP_THREADS), smem_, st, 2, tmA, tmBh, tmY, tmR, \
+                          p, nt, pairs) != cudaSuccess) {                                                                       \
                 am_set_error_("am_linear_tc: cluster launch failed");                                                           \
                 return AM_ELAUNCH;                                                                                              \
             }                                                                                                                   \
         } else                                                                                                                  \
-        gemm_tc_persistent_kernel<BN_, NST_, ACT_, MODE_><<<grid, TCP_THREADS, smem_, st>>>(tmA, tmB, tmY, tmR, p, nt, total);         \
+        am_launch(gemm_tc_persistent_kernel<BN_, NST_, ACT_, MODE_>, dim3(grid), dim3(TCP_THREADS), smem_, st, 1, tmA, tmB, tmY, tmR, p, nt, total); \
     } while (0)
         // epilogue mode: 1 / 2 = specialised fast paths of the big trunk GEMMs, 0 = general
         const int a15 = act & 15;

@@ -10,6 +10,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float* __restrict__ Y, int ldy, int M, int D, float eps,
                                                         __nv_bfloat16* __restrict__ Y2, int Np2) {
+    pdl_launch_dependents();
+    pdl_wait();
     int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= M) return;
     int lane = threadIdx.x & 31;
@@ -60,6 +62,8 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restr
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             float* __restrict__ Y, int ldy, int M, int D, float eps,
                                                             __nv_bfloat16* __restrict__ Y2, int Np2) {
+    pdl_launch_dependents();
+    pdl_wait();
     int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= M) return;
     int lane = threadIdx.x & 31;
@@ -117,19 +121,19 @@ extern "C" int am_layernorm(const float* X, int ldx, const float* R, int ldr, co
                      (!Y || (a16(Y) && ldy % 4 == 0)) && (!Y2 || (a16(Y2) && Np2 == D));
     if (vec) {
         switch (D / 128) {
-            case 1: layernorm_vec_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2); break;
-            case 2: layernorm_vec_kernel<2><<<grid, 256, 0, as_stream(stream)>>>(X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2); break;
-            case 4: layernorm_vec_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2); break;
-            case 8: layernorm_vec_kernel<8><<<grid, 256, 0, as_stream(stream)>>>(X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2); break;
+            case 1: am_launch(layernorm_vec_kernel<1>, dim3(grid), dim3(256), 0, as_stream(stream), 1, X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2); break;
+            case 2: am_launch(layernorm_vec_kernel<2>, dim3(grid), dim3(256), 0, as_stream(stream), 1, X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2); break;
+            case 4: am_launch(layernorm_vec_kernel<4>, dim3(grid), dim3(256), 0, as_stream(stream), 1, X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2); break;
+            case 8: am_launch(layernorm_vec_kernel<8>, dim3(grid), dim3(256), 0, as_stream(stream), 1, X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2); break;
             default: goto scalar_path;
         }
         AM_LAUNCH_CHECK("layernorm");
         return AM_OK;
     }
 scalar_path:
-    if (D <= 256) layernorm_kernel<8><<<grid, 256, 0, as_stream(stream)>>>(X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2);
-    else if (D <= 512) layernorm_kernel<16><<<grid, 256, 0, as_stream(stream)>>>(X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2);
-    else layernorm_kernel<32><<<grid, 256, 0, as_stream(stream)>>>(X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2);
+    if (D <= 256) am_launch(layernorm_kernel<8>, dim3(grid), dim3(256), 0, as_stream(stream), 1, X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2);
+    else if (D <= 512) am_launch(layernorm_kernel<16>, dim3(grid), dim3(256), 0, as_stream(stream), 1, X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2);
+    else am_launch(layernorm_kernel<32>, dim3(grid), dim3(256), 0, as_stream(stream), 1, X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2);
     AM_LAUNCH_CHECK("layernorm");
     return AM_OK;
 }

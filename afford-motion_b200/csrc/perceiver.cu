@@ -44,6 +44,8 @@ __global__ void __launch_bounds__(PW * 32, 1)
 cdm_encoder_partial_kernel(const float* __restrict__ x_t, const float* __restrict__ xyz, const float* __restrict__ w_ea,
                            const float* __restrict__ b_ea, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
                            const float* __restrict__ qf, int ldq, float* __restrict__ part, int N, int cx, int nchunk) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ __align__(16) float sm[];
     const int cin = cx + 3;
     float* Wt = sm;                 // [cin][C]
@@ -126,6 +128,8 @@ cdm_encoder_partial_kernel(const float* __restrict__ x_t, const float* __restric
 }
 
 __global__ void cdm_encoder_combine_kernel(const float* __restrict__ part, float* __restrict__ z, int nchunk) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.y, r = blockIdx.x, ch = threadIdx.x;
     const float* base = part + (int64_t)b * nchunk * R * (C + 2);
     float M = -CUDART_INF_F;
@@ -148,6 +152,8 @@ cdm_decoder_point_kernel(const float* __restrict__ x_t, const float* __restrict_
                          const float* __restrict__ kf, int ldk, const float* __restrict__ U, const float* __restrict__ bo,
                          const float* __restrict__ lnm_g, const float* __restrict__ lnm_b, float* __restrict__ h1,
                          float* __restrict__ hn, __nv_bfloat16* __restrict__ hn2, int N, int cx, int pts_per_cta) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ __align__(16) float sm[];
     const int cin = cx + 3;
     float* Wt = sm;                  // [cin][C]
@@ -226,6 +232,8 @@ cdm_decoder_point_kernel(const float* __restrict__ x_t, const float* __restrict_
 __global__ void __launch_bounds__(256)
 linear_skinny_kernel(const float* __restrict__ X1, int ldx1, int K1, const float* __restrict__ X2, int ldx2, int K2,
                      const float* __restrict__ W, const float* __restrict__ bias, float* __restrict__ Y, int ldy, int M, int N) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ __align__(16) float sw[];  // W [N][K1+K2]
     const int K = K1 + K2;
     for (int i = threadIdx.x; i < N * K; i += blockDim.x) sw[i] = W[i];
@@ -274,14 +282,14 @@ extern "C" int am_cdm_encoder_partial(const float* x_t, const float* xyz, const 
     size_t smem = sizeof(float) * ((size_t)(cx + 3) * C + (size_t)R * (C + 4) + (size_t)PW * R * (C + 2));
     int rc = opt_in_smem((const void*)cdm_encoder_partial_kernel, smem, "am_cdm_encoder_partial: shared memory");
     if (rc) return rc;
-    cdm_encoder_partial_kernel<<<dim3(nchunk, B), PW * 32, smem, as_stream(stream)>>>(x_t, xyz, w_ea, b_ea, ln_g, ln_b, qf, ldq, part, N, cx, nchunk);
+    am_launch(cdm_encoder_partial_kernel, dim3(dim3(nchunk, B)), dim3(PW * 32), smem, as_stream(stream), 1, x_t, xyz, w_ea, b_ea, ln_g, ln_b, qf, ldq, part, N, cx, nchunk);
     AM_LAUNCH_CHECK("cdm_encoder_partial");
     return AM_OK;
 }
 
 extern "C" int am_cdm_encoder_combine(const float* part, float* z, int B, int nchunk, am_stream_t stream) {
     AM_REQUIRE(part && z && B > 0 && nchunk > 0, AM_EINVAL, "am_cdm_encoder_combine: bad args");
-    cdm_encoder_combine_kernel<<<dim3(R, B), C, 0, as_stream(stream)>>>(part, z, nchunk);
+    am_launch(cdm_encoder_combine_kernel, dim3(dim3(R, B)), dim3(C), 0, as_stream(stream), 1, part, z, nchunk);
     AM_LAUNCH_CHECK("cdm_encoder_combine");
     return AM_OK;
 }
@@ -298,7 +306,7 @@ extern "C" int am_cdm_decoder_point(const float* x_t, const float* xyz, const fl
     // ~2 waves of CTAs over the 148 SMs (4 CTAs of 8 warps resident per SM)
     int pts = 64;
     while ((int64_t)cdiv(N, pts) * B > 148 * 8 && pts < 1024) pts *= 2;
-    cdm_decoder_point_kernel<<<dim3(cdiv(N, pts), B), PW * 32, smem, as_stream(stream)>>>(x_t, xyz, wd, bd, lnq_g, lnq_b, kf, ldk, U, bo,
+    am_launch(cdm_decoder_point_kernel, dim3(dim3(cdiv(N, pts), B)), dim3(PW * 32), smem, as_stream(stream), 1, x_t, xyz, wd, bd, lnq_g, lnq_b, kf, ldk, U, bo,
                                                                                           lnm_g, lnm_b, h1, hn, reinterpret_cast<__nv_bfloat16*>(hn2), N, cx, pts);
     AM_LAUNCH_CHECK("cdm_decoder_point");
     return AM_OK;
@@ -311,7 +319,7 @@ extern "C" int am_linear_skinny(const float* X1, int ldx1, int K1, const float* 
     size_t smem = sizeof(float) * (size_t)N * (K1 + K2);
     AM_REQUIRE(smem <= 48 * 1024, AM_EINVAL, "am_linear_skinny: weight does not fit shared memory");
     int grid = cdiv(M, 8) < 148 * 8 ? cdiv(M, 8) : 148 * 8;
-    linear_skinny_kernel<<<grid, 256, smem, as_stream(stream)>>>(X1, ldx1, K1, X2, ldx2, K2, W, bias, Y, ldy, M, N);
+    am_launch(linear_skinny_kernel, dim3(grid), dim3(256), smem, as_stream(stream), 1, X1, ldx1, K1, X2, ldx2, K2, W, bias, Y, ldy, M, N);
     AM_LAUNCH_CHECK("linear_skinny");
     return AM_OK;
 }

@@ -10,6 +10,7 @@ L.am_tc_set_tile_.argtypes = [ctypes.c_int, ctypes.c_int]
 L.am_tc_set_epi_.argtypes = [ctypes.c_int]
 L.am_tc_set_2sm_.argtypes = [ctypes.c_int]
 L.am_tc_set_bk_.argtypes = [ctypes.c_int]
+L.am_tc_set_mixed_.argtypes = [ctypes.c_int]
 dev = "cuda:0"
 M, D, FF = 32 * 326, 512, 1024
 g = torch.Generator(device=dev).manual_seed(0)
@@ -32,8 +33,9 @@ flops = {"qkv": 2 * M * 3 * D * D, "out": 2 * M * D * D, "ffn1": 2 * M * FF * D,
 ref_out = {}
 for name, fn in cases.items():
     row = []
-    for bn, cl, lsu, sm2, bk in ((0, 0, 0, 0, 32), (256, 0, 0, 0, 32), (0, 0, 0, 1, 32), (256, 0, 0, 1, 32), (0, 0, 0, 1, 64), (128, 0, 0, 1, 64), (256, 0, 0, 1, 64), (256, 0, 1, 1, 64)):
+    for bn, cl, lsu, sm2, bk, mixed in ((0, 0, 0, 0, 32, 0), (0, 0, 0, 1, 32, 0), (0, 0, 0, 1, 64, 0), (128, 0, 0, 1, 64, 0), (256, 0, 0, 1, 64, 0), (256, 0, 0, 1, 64, 1), (0, 0, 0, 1, 64, 1)):
         L.am_tc_set_tile_(bn, cl)
+        L.am_tc_set_mixed_(mixed)
         L.am_tc_set_bk_(bk)
         L.am_tc_set_epi_(lsu)
         L.am_tc_set_2sm_(sm2)
@@ -50,9 +52,10 @@ for name, fn in cases.items():
         if key not in ref_out:
             ref_out[key] = out
         same = bool(torch.equal(out, ref_out[key]))  # every variant must give bit-identical results (same accumulation order)
-        row.append(f"{'2SM' if sm2 else '1SM'} bk={bk} bn={bn or 'auto'} cl={cl} {'lsu' if lsu else 'tma'}: {us:6.1f} us ({flops[key] / us / 1e6:4.0f} TF/s){'' if same else ' MISMATCH'}")
+        row.append(f"{'2SM' if sm2 else '1SM'} bk={bk} bn={bn or 'auto'} {'mixed' if mixed else 'whole'} {'lsu' if lsu else 'tma'}: {us:6.1f} us ({flops[key] / us / 1e6:4.0f} TF/s){'' if same else ' MISMATCH'}")
     print(name + "\n   " + "\n   ".join(row))
 L.am_tc_set_tile_(0, -1)
 L.am_tc_set_epi_(-1)
 L.am_tc_set_2sm_(-1)
 L.am_tc_set_bk_(0)
+L.am_tc_set_mixed_(1)

@@ -36,8 +36,22 @@ d = dbg.cpu().tolist()
 t0 = d[0]
 if os.environ.get("AMB200_TC_VARIANT", "persistent") == "persistent":
     print("tile  mma_committed  epi_start  epi_end   (cycles since CTA 0 start; the CTA-pair kernel records commit and epi_end only)")
+    last = 0
     for it in range(6):
         print(it, *[(d[o + it] - t0 if d[o + it] else None) for o in (8, 40, 72)])
+        last = d[72 + it] - t0 if d[72 + it] else last
+    if d[1] and d[2]:
+        print(f"CTA 0: {last} cycles in {d[2] - d[1]} ns -> SM clock {1e3 * last / (d[2] - d[1]):.0f} MHz during this launch")
+    reps = 50
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    L.am_tc_set_debug_(None)
+    for _ in range(5):
+        run()
+    s.record()
+    for _ in range(reps):
+        run()
+    e.record(); torch.cuda.synchronize()
+    print(f"back-to-back launch period: {1e3 * s.elapsed_time(e) / reps:.1f} us")
     sys.exit(0)
 nkb = K // (64 if os.environ.get("AMB200_TC_VARIANT") == "64x3" else 32)
 print("prologue sync done +", d[1] - t0, " tmem_full seen +", d[2] - t0, " epilogue done +", d[3] - t0, " teardown +", d[4] - t0)
