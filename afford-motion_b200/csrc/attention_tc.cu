@@ -137,9 +137,16 @@ __device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) {
 __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
+// [V_hi | V_lo] as ONE MN-major B operand with N = 128: two 64-wide SW128 atoms, the second LBO = OFF_VL - OFF_VH bytes after
+// the first (same key rows of the lo tile) -> P_hi . [V_hi | V_lo] is a single MMA (the A slice is fetched from TMEM once).
+__device__ __forceinline__ uint64_t desc_mnmajor_hilo(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((3 * TILE_BYTES) >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
 // instruction descriptors (cute::UMMA::InstrDescriptor): F32 accum, BF16 A/B
 constexpr uint32_t IDESC_S = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 constexpr uint32_t IDESC_PV = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) /*B MN-major*/ | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+constexpr uint32_t IDESC_PV2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) /*B MN-major*/ | ((uint32_t)((2 * HD) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 mha_tc_kernel(const __grid_constant__ CUtensorMap tm, AttParams p) {
@@ -150,11 +157,11 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tm, AttParams p) {
     uint64_t* kv_full = bars + 0;
     uint64_t* q_full = bars + 1;
     uint64_t* q_empty = bars + 2;
-    uint64_t* s_full = bars + 3;
+    uint64_t* s_full = bars + 12;   // [3] one per 128-key tile: the row-max pass starts on key tile 0 while tiles 1, 2 are still in the tensor pipe
     uint64_t* o_full = bars + 4;
     uint64_t* acc_free = bars + 5;
     uint64_t* p_ready = bars + 6;   // [6] one per 64-key block
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 12);
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 16);
     uint32_t* maskbits = tmem_holder + 1;  // [12] bit k of word w: key 32w+k is attendable
     float* xchg = reinterpret_cast<float*>(maskbits + 12);  // [2][128] row max / row sum exchange between the two softmax groups
 
@@ -168,7 +175,8 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tm, AttParams p) {
     // 10 TMA producer, 11 MMA issuer
     if (warp == 10 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm)) : "memory");
     if (warp == 11 && lane == 0) {
-        mbar_init_a(kv_full, 1); mbar_init_a(q_full, 1); mbar_init_a(q_empty, 1); mbar_init_a(s_full, 1); mbar_init_a(o_full, 1);
+        mbar_init_a(kv_full, 1); mbar_init_a(q_full, 1); mbar_init_a(q_empty, 1); mbar_init_a(o_full, 1);
+        for (int j = 0; j < 3; ++j) mbar_init_a(&s_full[j], 1);
         mbar_init_a(acc_free, 256);
         for (int j = 0; j < 6; ++j) mbar_init_a(&p_ready[j], 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -238,8 +246,8 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tm, AttParams p) {
                         umma_ss(d, qh + ko, kl + ko, IDESC_S, 1u);
                         umma_ss(d, qh + ko, kh + ko, IDESC_S, 1u);
                     }
+                    umma_commit_a(&s_full[kt]);
                 }
-                umma_commit_a(s_full);
                 umma_commit_a(q_empty);
                 if (p.dbg && blockIdx.x == 0) p.dbg[16 + t] = clock64();
                 // ---- O = P V per 64-key block, P (bf16 hi | lo) read from TMEM where the softmax warps stored it
@@ -250,10 +258,12 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tm, AttParams p) {
                     const uint32_t voff = (uint32_t)(j * 64) * 128u;  // 64 keys * 128 B rows
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {  // 16 keys per MMA: A advances 8 TMEM columns, V advances 16 rows = 2048 B
-                        const uint64_t vh = desc_mnmajor(sb + OFF_VH + voff + k * 2048), vl = desc_mnmajor(sb + OFF_VL + voff + k * 2048);
-                        umma_ts(tmem_base + O_COL, a_lo + k * 8, vh, IDESC_PV, (j | k) ? 1u : 0u);
-                        umma_ts(tmem_base + O_COL, a_hi + k * 8, vl, IDESC_PV, 1u);
-                        umma_ts(tmem_base + O_COL, a_hi + k * 8, vh, IDESC_PV, 1u);
+                        // O[:, 0:128] += P_hi . [V_hi | V_lo]   (one MMA, N = 128);   O[:, 0:64] += P_lo . V_hi   (N = 64)
+                        // the epilogue adds the two 64-column halves.  Measured: three N = 64 MMAs per step ran at ~93 cycles each
+                        // (the 4 KB A slice comes from TMEM for every MMA); two MMAs fetch it twice instead of three times.
+                        const uint64_t vhl = desc_mnmajor_hilo(sb + OFF_VH + voff + k * 2048), vh = desc_mnmajor(sb + OFF_VH + voff + k * 2048);
+                        umma_ts(tmem_base + O_COL, a_hi + k * 8, vhl, IDESC_PV2, (j | k) ? 1u : 0u);
+                        umma_ts(tmem_base + O_COL, a_lo + k * 8, vh, IDESC_PV, 1u);
                     }
                 }
                 umma_commit_a(o_full);
@@ -270,12 +280,12 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tm, AttParams p) {
         for (int t = 0; t < nq; ++t) {
             const uint32_t pt = t & 1;
             const int qi = t * QT + r;
-            mbar_wait_a(s_full, pt);
-            fence_after_a();
-            if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[32 + t] = clock64();
             // pass 1: row max of the scaled scores over attendable keys (own blocks), then exchange with the other group
             float mx = -CUDART_INF_F;
             for (int j = grp; j < nblk; j += 2) {
+                mbar_wait_a(&s_full[j >> 1], pt);  // key tile j/2 of S is complete
+                fence_after_a();
+                if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0 && j == 0) p.dbg[32 + t] = clock64();
 #pragma unroll
                 for (int hlf = 0; hlf < 2; ++hlf) {
                     uint32_t v[32];
@@ -343,7 +353,13 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tm, AttParams p) {
             fence_after_a();
             if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[56 + t] = clock64();
             uint32_t o0[32];
-            tmem_ld32a(lane_addr + O_COL + grp * 32, o0);
+            {
+                uint32_t o1[32];
+                tmem_ld32a(lane_addr + O_COL + grp * 32, o0);
+                tmem_ld32a(lane_addr + O_COL + HD + grp * 32, o1);   // the P_hi . V_lo term
+#pragma unroll
+                for (int c = 0; c < 32; ++c) o0[c] = __float_as_uint(__uint_as_float(o0[c]) + __uint_as_float(o1[c]));
+            }
             fence_before_a();
             mbar_arrive_a(acc_free);  // S / O columns may be overwritten by the next query tile
             softmax_bar();            // xchg free for the next tile
