@@ -189,14 +189,14 @@ class CDMEngine:
         ops.layernorm(L0, w["e_qn_g"], w["e_qn_b"], ws["LN"], M2, DL)
         ops.linear(ws["LN"], w["e_q_w"], ws["Q"], M2, DL, DL, bias=w["e_q_b"])
         hd = DL // He
-        for h in range(He):  # qf[b, 2h+l, :C] = Wk_h^T q_{h,l} ; [.., C] = q_{h,l}.bk_h
-            ops.linear(ws["Q"][:, h * hd:], w["e_kfold"][h], ws["QF"], M2, C + 1, hd, ldx=DL, ldy=C + 4, ymap=(2, R, 2 * h))
+        # qf[b, 2h+l, :C] = Wk_h^T q_{h,l} ; [.., C] = q_{h,l}.bk_h      (all heads in one batched launch)
+        ops.linear_batched(ws["Q"], w["e_kfold"], ws["QF"], M2, C + 1, hd, He, hd, (C + 1) * hd, 2 * (C + 4), ldx=DL, ldy=C + 4,
+                           ymap=(2, R, 0))
         ops.cdm_encoder_partial(x, cond.xyz, w["ea_w"], w["ea_b"], w["e_kvn_g"], w["e_kvn_b"], ws["QF"], C + 4, ws["PART"], B, N, cx,
                                 ws["nchunk"])
         ops.cdm_encoder_combine(ws["PART"], ws["Z"], B, ws["nchunk"])
-        for h in range(He):  # o_{h,l} = Wv_h z_{h,l} + bv_h
-            ops.linear(ws["Z"], w["e_v_w"][h * hd:(h + 1) * hd], ws["AO"][:, h * hd:], M2, hd, C, bias=w["e_v_b"][h * hd:(h + 1) * hd],
-                       ldy=DL, xmap=(2, R, 2 * h))
+        # o_{h,l} = Wv_h z_{h,l} + bv_h
+        ops.linear_batched(ws["Z"], w["e_v_w"], ws["AO"], M2, hd, C, He, 2 * C, hd * C, hd, bias=w["e_v_b"], bb=hd, ldy=DL, xmap=(2, R, 0))
         ops.linear(ws["AO"], w["e_o_w"], ws["La"], M2, DL, DL, bias=w["e_o_b"], residual=L0)  # residual on un-normalised L (:230)
         ops.layernorm(ws["La"], w["e_m_g"], w["e_m_b"], ws["LN"], M2, DL)
         ops.linear(ws["LN"], w["e_m1_w"], ws["Hh"], M2, DL, DL, bias=w["e_m1_b"], act="gelu")
@@ -216,9 +216,9 @@ class CDMEngine:
         ops.layernorm(cur, w["d_kvn_g"], w["d_kvn_b"], ws["LN"], M2, DL)
         ops.linear(ws["LN"], w["d_kv_w"], ws["KV"], M2, 2 * C, DL, bias=w["d_kv_b"])
         hdd = self.hdd
-        for h in range(Hd):
-            ops.linear(ws["KV"][:, h * hdd:], w["d_qfold"][h], ws["KF"], M2, C + 1, hdd, ldx=2 * C, ldy=C + 4, ymap=(2, R, 2 * h))
-            ops.linear(ws["KV"][:, C + h * hdd:], w["d_o_w"][:, h * hdd:], ws["U"], M2, C, hdd, ldx=2 * C, ldw=C, ymap=(2, R, 2 * h))
+        ops.linear_batched(ws["KV"], w["d_qfold"], ws["KF"], M2, C + 1, hdd, Hd, hdd, (C + 1) * hdd, 2 * (C + 4), ldx=2 * C, ldy=C + 4,
+                           ymap=(2, R, 0))
+        ops.linear_batched(ws["KV"][:, C:], w["d_o_w"], ws["U"], M2, C, hdd, Hd, hdd, hdd, 2 * C, ldx=2 * C, ldw=C, ymap=(2, R, 0))
         ops.cdm_decoder_point(x, cond.xyz, w["dd_w"], w["dd_b"], w["d_qn_g"], w["d_qn_b"], ws["KF"], C + 4, ws["U"], w["d_o_b"],
                               w["d_m_g"], w["d_m_b"], ws["H1"], ws["HN"], B, N, cx, hn2=ws["HN2"])
         if self.gemm == "tc":  # the one dense per-point layer: 256 -> 256 GELU on the tensor cores

@@ -86,6 +86,16 @@ def linear(x, w, y, M, N, K, bias=None, act=None, residual=None, ldx=None, ldw=N
     return y
 
 
+def linear_batched(x, w, y, M, N, K, nbatch, xb, wb, yb, bias=None, bb=0, act=None, ldx=None, ldw=None, ldy=None, xmap=(0, 0, 0),
+                   ymap=(0, 0, 0)):
+    """nbatch independent linears in one launch (element strides xb / wb / yb / bb between batch entries); see am_linear_f32_batched."""
+    _chk_cuda(x, w, y)
+    _l.check(_l.load().am_linear_f32_batched(_ptr(x), K if ldx is None else ldx, _ptr(w), K if ldw is None else ldw, _ptr(y),
+                                            N if ldy is None else ldy, M, N, K, _ptr(bias), ACT[act], xmap[0], xmap[1], xmap[2],
+                                            ymap[0], ymap[1], ymap[2], nbatch, xb, wb, yb, bb, _stream()), "am_linear_f32_batched")
+    return y
+
+
 def layernorm(x, gamma, beta, y, M, D, residual=None, eps=1e-5, ldx=None, ldy=None, ldr=None, y2=None):
     _chk_cuda(x)
     _l.check(_l.load().am_layernorm(_ptr(x), D if ldx is None else ldx, _ptr(residual), D if ldr is None else ldr, _ptr(gamma),
@@ -268,7 +278,7 @@ def _wrap(name, fn):
     return wrapped
 
 
-for _n in ("randn_", "p_sample_update", "ddim_update", "q_sample", "masked_mse", "add_i32", "linear", "layernorm", "mha_fwd",
+for _n in ("randn_", "p_sample_update", "ddim_update", "q_sample", "masked_mse", "add_i32", "linear", "linear_batched", "layernorm", "mha_fwd",
            "gather_time_token", "gather_rows", "furthestsampling", "knnquery", "pt_layer_fwd", "transition_down_fwd", "interpolation", "segment_mean",
            "cdm_encoder_partial", "cdm_encoder_combine", "cdm_decoder_point", "linear_skinny", "split_bf16", "linear_tc", "mha_tc_fwd"):
     globals()[_n] = _wrap(_n, globals()[_n])

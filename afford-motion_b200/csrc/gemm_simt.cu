@@ -14,6 +14,7 @@ struct GemmParams {
     const float* residual; int ldr; int res_mod;
     int xin_g, xout_g, x_off, yin_g, yout_g, y_off;
     int vecA, vecB, vecY;
+    int64_t xb, wb, yb, bb;  // per-batch element strides (blockIdx.z) of X / W / Y / bias — small-M kernel only
 };
 
 __device__ __forceinline__ int64_t map_row(int m, int gin, int gout, int off) {
@@ -173,30 +174,141 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmParams p) {
     }
 }
 
+// Small-M variant (the 2-latent-token side of the CDM Perceiver: M = 2 B rows, and its per-head fold GEMMs).  The tiled kernel
+// above launches cdiv(N, 64) x cdiv(M, 64) CTAs — 8 CTAs for a [16 x 512] x [512 x 512] layer, each walking K serially: 16.6 us
+// per launch, 44 launches per denoise step = half of the CDM step at 8 samples per GPU.  Here parallelism comes from N: one warp
+// per output column, lanes split K (coalesced 128-bit reads of the weight row), the <= 16 activation rows of the CTA sit in
+// shared memory, 16 accumulators per lane, warp-shuffle reduction.  Same epilogue semantics (bias, activation, residual,
+// token row maps) as gemm_f32_kernel.
+constexpr int SM_ROWS = 16, SM_WARPS = 8;
+__global__ void __launch_bounds__(SM_WARPS * 32) gemm_smallm_kernel(GemmParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
+    extern __shared__ __align__(16) float xs[];  // [SM_ROWS][Kp], Kp = K rounded up to 4
+    const int Kp = (p.K + 3) & ~3;
+    const int m0 = blockIdx.y * SM_ROWS;
+    const int rows = min(SM_ROWS, p.M - m0);
+    {   // batch (blockIdx.z): the per-head fold GEMMs of the Perceiver differ only by pointer offsets
+        const int64_t z = blockIdx.z;
+        p.X += z * p.xb; p.W += z * p.wb; p.Y += z * p.yb;
+        if (p.bias) p.bias += z * p.bb;
+    }
+    if (p.vecA && (p.K & 3) == 0 && (p.xb & 3) == 0) {
+        const int k4n = Kp >> 2;
+        for (int i = threadIdx.x; i < SM_ROWS * k4n; i += blockDim.x) {
+            const int r = i / k4n, k4 = i - r * k4n;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < rows) v = *reinterpret_cast<const float4*>(p.X + map_row(m0 + r, p.xin_g, p.xout_g, p.x_off) * p.ldx + 4 * k4);
+            reinterpret_cast<float4*>(xs)[i] = v;
+        }
+    } else {
+        for (int i = threadIdx.x; i < SM_ROWS * Kp; i += blockDim.x) {
+            const int r = i / Kp, k = i - r * Kp;
+            float v = 0.f;
+            if (r < rows && k < p.K) v = p.X[map_row(m0 + r, p.xin_g, p.xout_g, p.x_off) * p.ldx + k];
+            xs[i] = v;
+        }
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.x * SM_WARPS + warp;
+    if (n >= p.N) return;
+    float acc[SM_ROWS];
+#pragma unroll
+    for (int r = 0; r < SM_ROWS; ++r) acc[r] = 0.f;
+    const float* wrow = p.W + (int64_t)n * p.ldw;
+    if (p.vecB && (p.wb & 3) == 0) {
+        for (int k = lane * 4; k < Kp; k += 128) {
+            float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k + 3 < p.K) w4 = *reinterpret_cast<const float4*>(wrow + k);
+            else { if (k < p.K) w4.x = wrow[k]; if (k + 1 < p.K) w4.y = wrow[k + 1]; if (k + 2 < p.K) w4.z = wrow[k + 2]; }
+#pragma unroll
+            for (int r = 0; r < SM_ROWS; ++r) {
+                const float4 x4 = *reinterpret_cast<const float4*>(xs + r * Kp + k);
+                acc[r] = fmaf(x4.x, w4.x, fmaf(x4.y, w4.y, fmaf(x4.z, w4.z, fmaf(x4.w, w4.w, acc[r]))));
+            }
+        }
+    } else {
+        for (int k = lane; k < p.K; k += 32) {
+            const float w = wrow[k];
+#pragma unroll
+            for (int r = 0; r < SM_ROWS; ++r) acc[r] = fmaf(xs[r * Kp + k], w, acc[r]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < SM_ROWS; ++r) acc[r] = warp_sum(acc[r]);
+    // lane r finishes output row m0 + r of column n
+    float x = 0.f;
+#pragma unroll
+    for (int r = 0; r < SM_ROWS; ++r) x = lane == r ? acc[r] : x;
+    if (lane < rows) {
+        const int m = m0 + lane;
+        const int64_t yrow = map_row(m, p.yin_g, p.yout_g, p.y_off);
+        if (p.bias) x += p.bias[n];
+        float rres = 0.f;
+        if (p.residual) rres = p.residual[(p.res_mod > 0 ? (int64_t)(m % p.res_mod) : yrow) * p.ldr + n];
+        if (p.act & AM_ACT_AFTER_RES) x = apply_act(x + rres, p.act & 15);
+        else x = apply_act(x, p.act) + rres;
+        p.Y[yrow * p.ldy + n] = x;
+    }
+}
+
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace
 
-extern "C" int am_linear_f32(const float* X, int ldx, const float* W, int ldw, float* Y, int ldy, int M, int N, int K, const float* bias,
+static int linear_f32_launch(const float* X, int ldx, const float* W, int ldw, float* Y, int ldy, int M, int N, int K, const float* bias,
                              int act, const float* residual, int ldr, int res_mod, int xin_g, int xout_g, int x_off, int yin_g,
-                             int yout_g, int y_off, am_stream_t stream) {
+                             int yout_g, int y_off, int nbatch, int64_t xb, int64_t wb, int64_t yb, int64_t bb, am_stream_t stream) {
     AM_REQUIRE(X && W && Y, AM_EINVAL, "am_linear_f32: null pointer");
-    AM_REQUIRE(M > 0 && N > 0 && K > 0 && ldx >= K && ldw >= K && ldy >= N, AM_EINVAL, "am_linear_f32: bad dims");
+    AM_REQUIRE(M > 0 && N > 0 && K > 0 && ldx >= K && ldw >= K && ldy >= N && nbatch >= 1, AM_EINVAL, "am_linear_f32: bad dims");
     AM_REQUIRE((act & 15) >= 0 && (act & 15) <= 3 && (act & ~31) == 0, AM_EINVAL, "am_linear_f32: bad activation");
     AM_REQUIRE(!residual || ldr >= N, AM_EINVAL, "am_linear_f32: bad residual stride");
-    GemmParams p{X, ldx, W, ldw, Y, ldy, M, N, K, bias, act, residual, ldr, res_mod, xin_g, xout_g, x_off, yin_g, yout_g, y_off, 0, 0, 0};
+    GemmParams p{X, ldx, W, ldw, Y, ldy, M, N, K, bias, act, residual, ldr, res_mod, xin_g, xout_g, x_off, yin_g, yout_g, y_off, 0, 0, 0,
+                 xb, wb, yb, bb};
     p.vecA = al16(X) && (ldx % 4 == 0);
     p.vecB = al16(W) && (ldw % 4 == 0);
     p.vecY = al16(Y) && (ldy % 4 == 0);
-    // tile choice: 128x128 when it still fills the 148 SMs, else 64x64
-    int64_t tiles128 = (int64_t)cdiv(M, 128) * cdiv(N, 128);
-    if (tiles128 >= AM_NUM_SMS) {
-        dim3 grid(cdiv(N, 128), cdiv(M, 128));
-        am_launch(gemm_f32_kernel<128, 128>, dim3(grid), dim3(256), 0, as_stream(stream), 1, p);
-    } else {
-        dim3 grid(cdiv(N, 64), cdiv(M, 64));
-        am_launch(gemm_f32_kernel<64, 64>, dim3(grid), dim3(256), 0, as_stream(stream), 1, p);
+    // small M (latent tokens): column-parallel kernel when the tiled one would launch only a handful of CTAs
+    const size_t sm_smem = sizeof(float) * SM_ROWS * (size_t)((K + 3) & ~3);
+    if (M <= 128 && (int64_t)cdiv(M, 64) * cdiv(N, 64) < 32 && sm_smem <= 48 * 1024) {
+        AM_REQUIRE(nbatch == 1 || !residual, AM_EINVAL, "am_linear_f32_batched: residual is not supported with nbatch > 1");
+        am_launch(gemm_smallm_kernel, dim3(cdiv(N, SM_WARPS), cdiv(M, SM_ROWS), nbatch), dim3(SM_WARPS * 32), sm_smem, as_stream(stream), 1, p);
+        AM_LAUNCH_CHECK("linear_f32");
+        return AM_OK;
     }
-    AM_LAUNCH_CHECK("linear_f32");
+    for (int z = 0; z < nbatch; ++z) {  // large shapes: one tiled launch per batch entry
+        GemmParams q = p;
+        q.X += z * xb; q.W += z * wb; q.Y += z * yb;
+        if (q.bias) q.bias += z * bb;
+        q.vecA = al16(q.X) && (ldx % 4 == 0);
+        q.vecB = al16(q.W) && (ldw % 4 == 0);
+        q.vecY = al16(q.Y) && (ldy % 4 == 0);
+        // tile choice: 128x128 when it still fills the 148 SMs, else 64x64
+        int64_t tiles128 = (int64_t)cdiv(M, 128) * cdiv(N, 128);
+        if (tiles128 >= AM_NUM_SMS) {
+            dim3 grid(cdiv(N, 128), cdiv(M, 128));
+            am_launch(gemm_f32_kernel<128, 128>, dim3(grid), dim3(256), 0, as_stream(stream), 1, q);
+        } else {
+            dim3 grid(cdiv(N, 64), cdiv(M, 64));
+            am_launch(gemm_f32_kernel<64, 64>, dim3(grid), dim3(256), 0, as_stream(stream), 1, q);
+        }
+        AM_LAUNCH_CHECK("linear_f32");
+    }
     return AM_OK;
+}
+
+extern "C" int am_linear_f32(const float* X, int ldx, const float* W, int ldw, float* Y, int ldy, int M, int N, int K, const float* bias,
+                             int act, const float* residual, int ldr, int res_mod, int xin_g, int xout_g, int x_off, int yin_g,
+                             int yout_g, int y_off, am_stream_t stream) {
+    return linear_f32_launch(X, ldx, W, ldw, Y, ldy, M, N, K, bias, act, residual, ldr, res_mod, xin_g, xout_g, x_off, yin_g, yout_g, y_off,
+                             1, 0, 0, 0, 0, stream);
+}
+
+extern "C" int am_linear_f32_batched(const float* X, int ldx, const float* W, int ldw, float* Y, int ldy, int M, int N, int K,
+                                     const float* bias, int act, int xin_g, int xout_g, int x_off, int yin_g, int yout_g, int y_off,
+                                     int nbatch, int64_t x_bstride, int64_t w_bstride, int64_t y_bstride, int64_t bias_bstride,
+                                     am_stream_t stream) {
+    return linear_f32_launch(X, ldx, W, ldw, Y, ldy, M, N, K, bias, act, nullptr, 0, 0, xin_g, xout_g, x_off, yin_g, yout_g, y_off, nbatch,
+                             x_bstride, w_bstride, y_bstride, bias_bstride, stream);
 }

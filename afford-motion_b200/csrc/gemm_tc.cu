@@ -403,6 +403,69 @@ __device__ __forceinline__ void epilogue_tile_fast(const TcParams& p, uint32_t t
     }
 }
 
+// MODE 5: the fast LSU epilogue with a token ROW MAP and a row-broadcast residual (motion_adapter: rows (b, t) of x_t land on
+// token rows b*S + 2+G + t, residual = positional encoding row t), fp32 and / or bf16 (hi|lo) outputs.  Same 16-byte lane
+// mapping as MODE 2 (8 lanes per row, 4 rows per warp instruction); the general MODE 0 path moves 8 bytes per lane with a
+// shuffle-dependent address per row and took 34 us for this 1.8 GFLOP GEMM.
+template <int ACT, int NCOLS>
+__device__ __forceinline__ void epilogue_tile_fast_mapped(const TcParams& p, uint32_t tmem_tile, int m0, int n0, int q, int half, int lane,
+                                                          uint32_t stage_u32) {
+    const int m_base = m0 + q * 32;
+    const int rsel = lane >> 3, ch = lane & 7;
+#pragma unroll 1
+    for (int blk = 0; blk < NCOLS / 64; ++blk) {
+        const int col0 = half * (NCOLS / 2) + blk * 32;
+        const int n = n0 + col0 + 4 * ch;
+        __syncwarp();
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            uint32_t v[16];
+            tmem_ld16(tmem_tile + ((uint32_t)(q * 32) << 16) + (uint32_t)(col0 + g * 16), v);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int c4 = g * 4 + k;
+                const uint32_t a = stage_u32 + lane * 128 + ((c4 ^ (lane & 7)) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v[4 * k]), "r"(v[4 * k + 1]), "r"(v[4 * k + 2]), "r"(v[4 * k + 3]) : "memory");
+            }
+        }
+        __syncwarp();
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+        float4 xv[8], rv[8];
+        int64_t yrow[8];
+        bool ok[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + rsel, m = m_base + r;
+            const uint32_t a = stage_u32 + r * 128 + ((ch ^ (r & 7)) << 4);
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(xv[i].x), "=f"(xv[i].y), "=f"(xv[i].z), "=f"(xv[i].w) : "r"(a) : "memory");
+            bool map_ok = true;
+            ok[i] = m < p.M;
+            yrow[i] = ok[i] ? map_row_tc(m, p.yin_g, p.yout_g, p.y_off, map_ok) : 0;
+            ok[i] = ok[i] && map_ok;
+            rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.residual && ok[i])
+                rv[i] = *reinterpret_cast<const float4*>(p.residual + (p.res_mod > 0 ? (int64_t)(m % p.res_mod) : yrow[i]) * p.ldr + n);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (!ok[i]) continue;
+            const float x0 = act_ct<ACT>(xv[i].x + bv.x) + rv[i].x, x1 = act_ct<ACT>(xv[i].y + bv.y) + rv[i].y;
+            const float x2 = act_ct<ACT>(xv[i].z + bv.z) + rv[i].z, x3 = act_ct<ACT>(xv[i].w + bv.w) + rv[i].w;
+            if (p.Y) *reinterpret_cast<float4*>(p.Y + yrow[i] * p.ldy + n) = make_float4(x0, x1, x2, x3);
+            if (p.Y2) {
+                __nv_bfloat162 h01 = __floats2bfloat162_rn(x0, x1), h23 = __floats2bfloat162_rn(x2, x3);
+                const uint32_t u01 = *reinterpret_cast<uint32_t*>(&h01), u23 = *reinterpret_cast<uint32_t*>(&h23);
+                __nv_bfloat162 l01 = __floats2bfloat162_rn(x0 - __uint_as_float(u01 << 16), x1 - __uint_as_float(u01 & 0xffff0000u));
+                __nv_bfloat162 l23 = __floats2bfloat162_rn(x2 - __uint_as_float(u23 << 16), x3 - __uint_as_float(u23 & 0xffff0000u));
+                uint2* hi = reinterpret_cast<uint2*>(p.Y2 + yrow[i] * (2 * (int64_t)p.Np2) + n);
+                hi[0] = make_uint2(u01, u23);
+                hi[p.Np2 / 4] = make_uint2(*reinterpret_cast<uint32_t*>(&l01), *reinterpret_cast<uint32_t*>(&l23));
+            }
+        }
+    }
+}
+
 // TMA-store epilogue (MODE 3, the bf16 (hi|lo)-only outputs of in_proj / FFN1).  Measured: LSU global stores of the
 // epilogue throttle the main loop (12.6K -> 17K cycles per 128x256 tile) and cost 6K of the epilogue's 10K cycles,
 // whatever their cache policy; handing the writes to the TMA engine removes the LSU from the output path entirely:
@@ -767,7 +830,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             if (dbg && threadIdx.x == 0 && it < 16) p.dbg[40 + it] = clock64();
             if (MODE == 3) epilogue_tile_tma<ACT, BN_>(p, &tmY, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane, smem_u32(stage_buf + warp * (32 * 32)));
             else if (MODE == 0) epilogue_tile_coalesced<ACT, BN_>(p, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane, stage_buf + warp * (32 * 32));
-            else epilogue_tile_fast<ACT, BN_, MODE>(p, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane, smem_u32(stage_buf + warp * (32 * 32)));
+            else if (MODE == 5) epilogue_tile_fast_mapped<ACT, BN_>(p, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane, smem_u32(stage_buf + warp * (32 * 32)));
+                else epilogue_tile_fast<ACT, BN_, MODE>(p, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane, smem_u32(stage_buf + warp * (32 * 32)));
             tc_fence_before();
             mbar_arrive(&tmem_empty[ab]);
             if (dbg && threadIdx.x == 0 && it < 16) p.dbg[72 + it] = clock64();
@@ -911,7 +975,8 @@ gemm_tc_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             if (dbg && threadIdx.x == 0 && it < 16) p.dbg[40 + it] = clock64();
             if (MODE == 3) epilogue_tile_tma<ACT, BN_>(p, &tmY, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane, smem_u32(stage_buf + warp * (32 * 32)));
             else if (MODE == 0) epilogue_tile_coalesced<ACT, BN_>(p, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane, stage_buf + warp * (32 * 32));
-            else epilogue_tile_fast<ACT, BN_, MODE>(p, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane, smem_u32(stage_buf + warp * (32 * 32)));
+            else if (MODE == 5) epilogue_tile_fast_mapped<ACT, BN_>(p, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane, smem_u32(stage_buf + warp * (32 * 32)));
+                else epilogue_tile_fast<ACT, BN_, MODE>(p, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane, smem_u32(stage_buf + warp * (32 * 32)));
             tc_fence_before();
             mbar_arrive(&tmem_empty[ab]);
             if (dbg && threadIdx.x == 0 && it < 16) p.dbg[72 + it] = clock64();
@@ -1100,6 +1165,7 @@ gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 if (MODE == 3 && narrow) epilogue_tile_tma<ACT, BN_ / 2>(p, &tmY, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane, smem_u32(stage_buf + warp * (32 * 32)));
                 else if (MODE == 3) epilogue_tile_tma<ACT, BN_>(p, &tmY, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane, smem_u32(stage_buf + warp * (32 * 32)));
                 else if (MODE == 0) epilogue_tile_coalesced<ACT, BN_>(p, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane, stage_buf + warp * (32 * 32));
+                else if (MODE == 5) epilogue_tile_fast_mapped<ACT, BN_>(p, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane, smem_u32(stage_buf + warp * (32 * 32)));
                 else epilogue_tile_fast<ACT, BN_, MODE>(p, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane, smem_u32(stage_buf + warp * (32 * 32)));
             }
             tc_fence_before();
@@ -1343,6 +1409,11 @@ extern "C" int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp
             };
             if (f32map(&tmY, Y, ldy) && (!residual || f32map(&tmR, residual, ldr))) mode = 4;
         }
+        // MODE 5: row-mapped / broadcast-residual outputs with 16-byte rows (motion_adapter)
+        if (mode == 0 && (yin_g > 0 || res_mod > 0) && (N % bn) == 0 && !(act & AM_ACT_AFTER_RES) && (a15 == AM_ACT_NONE || a15 == AM_ACT_GELU) &&
+            (!bias || (reinterpret_cast<uintptr_t>(bias) & 15u) == 0) &&
+            (!Y || ((ldy % 4) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15u) == 0)) &&
+            (!residual || ((ldr % 4) == 0 && (reinterpret_cast<uintptr_t>(residual) & 15u) == 0))) mode = 5;
 #define AM_TCP_BY_MODE(BN_, NST_)                                                                  \
     if (mode == 3 && a15 == AM_ACT_GELU) AM_TCP_LAUNCH(BN_, NST_, AM_ACT_GELU, 3);                  \
     else if (mode == 3) AM_TCP_LAUNCH(BN_, NST_, AM_ACT_NONE, 3);                                   \
@@ -1350,6 +1421,8 @@ extern "C" int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp
     else if (mode == 1) AM_TCP_LAUNCH(BN_, NST_, AM_ACT_NONE, 1);                                   \
     else if (mode == 4 && a15 == AM_ACT_GELU) AM_TCP_LAUNCH(BN_, NST_, AM_ACT_GELU, 4);             \
     else if (mode == 4) AM_TCP_LAUNCH(BN_, NST_, AM_ACT_NONE, 4);                                   \
+    else if (mode == 5 && a15 == AM_ACT_GELU) AM_TCP_LAUNCH(BN_, NST_, AM_ACT_GELU, 5);             \
+    else if (mode == 5) AM_TCP_LAUNCH(BN_, NST_, AM_ACT_NONE, 5);                                   \
     else if (mode == 2 && a15 == AM_ACT_GELU) AM_TCP_LAUNCH(BN_, NST_, AM_ACT_GELU, 2);             \
     else if (mode == 2) AM_TCP_LAUNCH(BN_, NST_, AM_ACT_NONE, 2);                                   \
     else switch (a15) {                                                                            \

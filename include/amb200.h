@@ -98,6 +98,14 @@ int am_linear_f32(const float* X, int ldx, const float* W, int ldw, float* Y, in
                   const float* bias, int act, const float* residual, int ldr, int res_mod,
                   int xin_g, int xout_g, int x_off, int yin_g, int yout_g, int y_off, am_stream_t stream);
 
+/* nbatch independent am_linear_f32 problems in ONE launch: entry z uses X + z*x_bstride, W + z*w_bstride, Y + z*y_bstride,
+ * bias + z*bias_bstride (element strides).  The per-head fold GEMMs of the CDM Perceiver (amb200.cdm_engine: 4 x 8 heads per
+ * denoise step, M = 2 latent rows per sample) are this shape.  No residual. */
+int am_linear_f32_batched(const float* X, int ldx, const float* W, int ldw, float* Y, int ldy, int M, int N, int K,
+                          const float* bias, int act, int xin_g, int xout_g, int x_off, int yin_g, int yout_g, int y_off,
+                          int nbatch, int64_t x_bstride, int64_t w_bstride, int64_t y_bstride, int64_t bias_bstride,
+                          am_stream_t stream);
+
 /* Y = LayerNorm(X (+ R)) * gamma + beta, eps inside sqrt (torch.nn.LayerNorm); rows of length D <= 1024 */
 int am_layernorm(const float* X, int ldx, const float* R, int ldr, const float* gamma, const float* beta,
                  float* Y, int ldy, int M, int D, float eps, void* Y2, int Np2, am_stream_t stream);

@@ -156,7 +156,8 @@ def test_pointops_module_api_matches_golden(golden_dir):
 
 
 # ------------------------------------------------------------------ dense building blocks vs torch fp32 reference
-@pytest.mark.parametrize("M,N,K", [(10432, 1536, 512), (392, 263, 512), (5, 7, 3), (392, 512, 263), (130, 1024, 512)])
+@pytest.mark.parametrize("M,N,K", [(10432, 1536, 512), (392, 263, 512), (5, 7, 3), (392, 512, 263), (130, 1024, 512),
+                                   (16, 512, 512), (16, 257, 64), (128, 512, 512), (33, 96, 130), (2, 1536, 512)])  # last five: small-M kernel
 def test_linear_f32_vs_torch(M, N, K):
     g = torch.Generator().manual_seed(M + N + K)
     x, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
@@ -200,6 +201,35 @@ def test_linear_tc_vs_fp64(M, N, K):
     y3 = torch.empty(M, N, device=DEV)
     ops.linear_tc(a2, w2, M, N, Kp, y=y3, bias=_cuda(b), act="relu_after_res", residual=_cuda(r))
     assert (y1 - y3).abs().max() < 1e-4
+
+
+def test_linear_small_m_strided_views_and_maps():
+    """The CDM latent-side calls: strided x / w views (per-head column slices), unaligned weight rows, token row maps on both
+    sides — all through the small-M kernel (M = 2B rows)."""
+    g = torch.Generator().manual_seed(9)
+    B, R, C, hd, DL = 8, 16, 256, 64, 512
+    M2 = 2 * B
+    Q = torch.randn(M2, DL, generator=g)
+    kfold = torch.randn(8, C + 1, hd, generator=g)
+    QF = torch.zeros(B, R, C + 4)
+    want = QF.clone()
+    Qd, kd, QFd = _cuda(Q), _cuda(kfold), _cuda(QF)
+    for h in range(8):  # amb200.cdm_engine: qf[b, 2h+l, :C+1] = kfold[h] q_{h,l}
+        ops.linear(Qd[:, h * hd:], kd[h], QFd, M2, C + 1, hd, ldx=DL, ldy=C + 4, ymap=(2, R, 2 * h))
+        y = Q[:, h * hd:(h + 1) * hd].double() @ kfold[h].double().T          # [M2, C+1]
+        want.view(B, R, C + 4)[:, 2 * h:2 * h + 2, :C + 1] = y.view(B, 2, C + 1).float()
+    assert (QFd.cpu() - want).abs().max() < 2e-5
+    # xmap + column-offset output + unaligned (odd ldw) weight rows
+    Z = torch.randn(B, R, C, generator=g)
+    Wv = torch.randn(DL, C + 1, generator=g)[:, :C]                              # ldw = C + 1: rows not 16-byte aligned
+    AO = torch.zeros(M2, DL)
+    Zd, Wd, AOd = _cuda(Z), _cuda(Wv.contiguous()), _cuda(AO)
+    Wodd = _cuda(torch.randn(DL, C + 1, generator=torch.Generator().manual_seed(10)))
+    for h in range(8):
+        ops.linear(Zd, Wodd[h * hd:(h + 1) * hd], AOd[:, h * hd:], M2, hd, C, ldw=C + 1, ldy=DL, xmap=(2, R, 2 * h))
+        zin = Z[:, 2 * h:2 * h + 2, :].reshape(M2, C).double()
+        AO[:, h * hd:(h + 1) * hd] = (zin @ Wodd[h * hd:(h + 1) * hd, :C].cpu().double().T).float()
+    assert (AOd.cpu() - AO).abs().max() < 2e-5
 
 
 def test_linear_tc_row_maps():

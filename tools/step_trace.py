@@ -11,15 +11,28 @@ from amb200.config import cmdm_model_cfg, full_cfg
 from models.base import create_model_and_diffusion
 from models.functions import set_text_feature_provider
 dev = torch.device("cuda:0")
-nd = int(sys.argv[1]) if len(sys.argv) > 1 else 200
-model, diff = create_model_and_diffusion(full_cfg(cmdm_model_cfg(Bn.NPTS), steps=nd), device=dev)
-model.load_state_dict(synth.fill_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed=0), strict=False)
-model.to(dev).eval()
-host = Bn.synth_host_inputs(0)
-txt = host["text"].to(dev)
-set_text_feature_provider(lambda raw: txt)
-kw = dict(c_text=host["texts"], c_pc_xyz=host["xyz"].to(dev), c_pc_contact=host["contact"].to(dev), x_mask=host["x_mask"].to(dev))
-job = lambda: diff.p_sample_loop(model, (Bn.B, Bn.T, Bn.DM), clip_denoised=False, model_kwargs=kw)
+which = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].isdigit() else "cmdm"
+nums = [int(a) for a in sys.argv[1:] if a.isdigit()]
+if which == "cmdm":   # python tools/step_trace.py [cmdm] [denoise_steps]
+    nd = nums[0] if nums else 200
+    model, diff = create_model_and_diffusion(full_cfg(cmdm_model_cfg(Bn.NPTS), steps=nd), device=dev)
+    model.load_state_dict(synth.fill_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed=0), strict=False)
+    model.to(dev).eval()
+    host = Bn.synth_host_inputs(0)
+    txt = host["text"].to(dev)
+    set_text_feature_provider(lambda raw: txt)
+    kw = dict(c_text=host["texts"], c_pc_xyz=host["xyz"].to(dev), c_pc_contact=host["contact"].to(dev), x_mask=host["x_mask"].to(dev))
+    job = lambda: diff.p_sample_loop(model, (Bn.B, Bn.T, Bn.DM), clip_denoised=False, model_kwargs=kw)
+else:                 # python tools/step_trace.py cdm [batch]   (BASELINE config 3: 100-step DDIM of a 500-step process, N=8192)
+    from amb200.config import cdm_model_cfg
+    Bc = nums[0] if nums else 8
+    model, diff = create_model_and_diffusion(full_cfg(cdm_model_cfg(Bn.NPTS), steps=500, timestep_respacing="ddim100"), device=dev)
+    model.load_state_dict(synth.fill_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed=0), strict=False)
+    model.to(dev).eval()
+    txt = synth.text_features(Bc, seed=3).to(dev)
+    set_text_feature_provider(lambda raw: txt)
+    kw = dict(c_text=[f"p{i}" for i in range(Bc)], c_pc_xyz=synth.scene_points(Bc, Bn.NPTS, seed=3).to(dev), c_pc_feat=None)
+    job = lambda: diff.ddim_sample_loop(model, (Bc, Bn.NPTS, 6), clip_denoised=False, model_kwargs=kw, eta=0.0)
 for _ in range(2):
     job()
 torch.cuda.synchronize()
