@@ -258,18 +258,18 @@ class BatchNormTrainFn(Function):
         M, C = x.shape
         dev = x.device
         sync = isinstance(bn, torch.nn.SyncBatchNorm) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-        acc = torch.zeros(2 * C, dtype=torch.float64, device=dev)
+        acc = torch.zeros(2 * C + 1, dtype=torch.float64, device=dev)
         mean, invstd, var = (torch.empty(C, device=dev) for _ in range(3))
-        Mtot = M
+        cnt = None
         if sync:
-            # global statistics: sum / sumsq over all ranks, then finalize with the global count
+            # global statistics: (sum, sumsq, row count) over all ranks in ONE all-reduce; the count stays on the device — a
+            # host read here (.item()) would drain the GPU once per BatchNorm layer, 28 times per CMDM training step
             _l.check(L().am_bn_train_stats(_p(x), M, C, float(bn.eps), _p(acc), _p(mean), _p(invstd), _p(var), _st()), "am_bn_train_stats")
-            cnt = torch.tensor([float(M)], dtype=torch.float64, device=dev)
+            acc[2 * C:].fill_(float(M))
             dist.all_reduce(acc)
-            dist.all_reduce(cnt)
-            Mtot = int(cnt.item())
-            mu = acc[:C] / Mtot
-            v = (acc[C:] / Mtot - mu * mu).clamp_min(0)
+            cnt = acc[2 * C:]
+            mu = acc[:C] / cnt
+            v = (acc[C:2 * C] / cnt - mu * mu).clamp_min(0)
             mean, var, invstd = mu.float(), v.float(), (1.0 / torch.sqrt(v + bn.eps)).float()
         else:
             _l.check(L().am_bn_train_stats(_p(x), M, C, float(bn.eps), _p(acc), _p(mean), _p(invstd), _p(var), _st()), "am_bn_train_stats")
@@ -279,10 +279,11 @@ class BatchNormTrainFn(Function):
             with torch.no_grad():
                 mom = bn.momentum if bn.momentum is not None else 0.1
                 bn.running_mean.mul_(1 - mom).add_(mean, alpha=mom)
-                bn.running_var.mul_(1 - mom).add_(var * (Mtot / max(Mtot - 1, 1)), alpha=mom)
+                unbias = (cnt / (cnt - 1).clamp_min(1)).float() if sync else M / max(M - 1, 1)
+                bn.running_var.mul_(1 - mom).add_(var * unbias, alpha=mom)
                 bn.num_batches_tracked += 1
         ctx.save_for_backward(x, y if relu else x, mean, invstd, gamma)
-        ctx.relu, ctx.sync, ctx.Mtot = relu, sync, Mtot
+        ctx.relu, ctx.sync, ctx.cnt = relu, sync, cnt
         return y
 
     @staticmethod
@@ -302,9 +303,12 @@ class BatchNormTrainFn(Function):
             _l.check(L().am_bn_bwd_reduce(_p(dy), _p(x), _p(y), _p(mean), _p(invstd), _p(acc), M, C, int(ctx.relu), _st()), "am_bn_bwd_reduce")
             db, dg = acc[:C].float(), acc[C:].float()
             dist.all_reduce(acc)
+            # the kernel divides by its integer row count: scale the global sums by M_local / M_global on the device instead
+            # of reading the global count back to the host
+            acc = acc * (float(M) / ctx.cnt)
             scratch_g, scratch_b = torch.zeros(C, device=dy.device), torch.zeros(C, device=dy.device)
             _l.check(L().am_bn_bwd_apply(_p(dy), _p(x), _p(y), _p(mean), _p(invstd), _p(gamma), _p(acc), _p(dx), _p(scratch_g), _p(scratch_b), M,
-                                         ctx.Mtot, C, int(ctx.relu), _st()), "am_bn_bwd_apply")
+                                         M, C, int(ctx.relu), _st()), "am_bn_bwd_apply")
         return dx, dg, db, None, None
 
 
