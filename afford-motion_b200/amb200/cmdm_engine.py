@@ -211,7 +211,7 @@ class CMDMEngine:
         if ws["xS"] is None or ws["xS"].shape[0] != B * T:
             ws["xS"] = torch.zeros(B * T, 2 * Kx, dtype=torch.bfloat16, device=x.device)
         ops.split_bf16(x, B * T, Dm, out=ws["xS"])
-        ops.linear_tc(ws["xS"], w["motion_adapter.w2"], B * T, D, Kx, y=X0, y2=X0S, bias=w["motion_adapter.b"],
+        ops.linear_tc(ws["xS"], w["motion_adapter.w2"], B * T, D, Kx, y=None, y2=X0S, bias=w["motion_adapter.b"],
                       residual=w["pe"][2 + G:2 + G + T], ldr=D, res_mod=T, ymap=(T, S, 2 + G), ldy=D, Np2=D)
         cur, curS = X0.view(M, D), X0S
         ffp = ops.pad32(self.ff)
@@ -225,11 +225,13 @@ class CMDMEngine:
             else:
                 ops.linear_tc(curS, w[p + "in_w2"], M, 3 * D, D, y=ws["QKV"], bias=w[p + "in_b"])
                 ops.mha_fwd(ws["QKV"], None, cond.key_pad, B, S, H, hd, 1.0 / math.sqrt(hd), out2=ws["ATTS"])
-            ops.linear_tc(ws["ATTS"], w[p + "out_w2"], M, D, D, y=ws["TMP"], bias=w[p + "out_b"], residual=cur)
-            ops.layernorm(ws["TMP"], w[p + "n1g"], w[p + "n1b"], ws["Y1"], M, D, eps=w[p + "eps1"], y2=ws["Y1S"])
+            # residual streams travel as the bf16 (hi|lo) pairs the LayerNorm / adapter epilogues already write for the next
+            # GEMM's A operand (x = hi + lo, 16 significant bits): no fp32 copy of the activations is written at all
+            ops.linear_tc(ws["ATTS"], w[p + "out_w2"], M, D, D, y=ws["TMP"], bias=w[p + "out_b"], residual_split=curS)
+            ops.layernorm(ws["TMP"], w[p + "n1g"], w[p + "n1b"], None, M, D, eps=w[p + "eps1"], y2=ws["Y1S"])
             ops.linear_tc(ws["Y1S"], w[p + "w12"], M, self.ff, D, y2=ws["FFS"], bias=w[p + "b1"], act="gelu", Np2=ffp)
-            ops.linear_tc(ws["FFS"], w[p + "w22"], M, D, ffp, y=ws["TMP"], bias=w[p + "b2"], residual=ws["Y1"])
-            ops.layernorm(ws["TMP"], w[p + "n2g"], w[p + "n2b"], None if last else nxt, M, D, eps=w[p + "eps2"], y2=nxtS)
+            ops.linear_tc(ws["FFS"], w[p + "w22"], M, D, ffp, y=ws["TMP"], bias=w[p + "b2"], residual_split=ws["Y1S"])
+            ops.layernorm(ws["TMP"], w[p + "n2g"], w[p + "n2b"], None, M, D, eps=w[p + "eps2"], y2=nxtS)
             cur, curS = nxt, nxtS
         if out is None:
             out = torch.empty(B, T, Dm, device=x.device)

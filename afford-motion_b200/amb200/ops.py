@@ -213,9 +213,13 @@ def split_bf16(x, M, K, out=None, ldx=None):
     return out
 
 
-def linear_tc(a2, w2, M, N, Kp, y=None, y2=None, bias=None, act=None, residual=None, ldr=0, res_mod=0, ldy=None, ymap=(0, 0, 0), Np2=0):
-    """tcgen05 GEMM on split-bf16 operands (see am_linear_tc)."""
+def linear_tc(a2, w2, M, N, Kp, y=None, y2=None, bias=None, act=None, residual=None, ldr=0, res_mod=0, ldy=None, ymap=(0, 0, 0), Np2=0,
+              residual_split=None):
+    """tcgen05 GEMM on split-bf16 operands (see am_linear_tc).  residual_split: bf16 (hi|lo) tensor [M, 2*N] added as hi + lo."""
     _chk_cuda(a2, w2)
+    if residual_split is not None:
+        assert residual is None
+        residual, ldr, res_mod = residual_split, residual_split.shape[-1] // 2, -1
     if residual is not None and ldr == 0:
         ldr = N
     if y2 is not None and Np2 == 0:

@@ -41,6 +41,7 @@ struct TcParams {
     __nv_bfloat16* Y2; int Np2;
     int vecY;
     long long* dbg;  // optional timeline buffer (tools/tc_timeline.py): CTA (0,0) records clock64() per role
+    int res_split;   // MODE 4: `residual` is a bf16 (hi|lo) split tensor [M, 2*ldr] (the previous LayerNorm's only output), not fp32
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -542,13 +543,6 @@ __device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
         if (++spins > 200000000u) __trap();
     }
 }
-__device__ __forceinline__ void tma_load_2d_s(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-
 template <int ACT, int NCOLS>
 __device__ __forceinline__ void epilogue_tile_tma_f32(const TcParams& p, const CUtensorMap* tmYf, const CUtensorMap* tmR, uint32_t tmem_tile,
                                                       int m0, int n0, int q, int half, int lane, uint32_t buf_u32 /* 2 x 2 KB */,
@@ -559,11 +553,25 @@ __device__ __forceinline__ void epilogue_tile_tma_f32(const TcParams& p, const C
     const bool rows_ok = m_base < p.M;
     const bool has_res = p.residual != nullptr;
     const int ncol0 = n0 + half * (NCOLS / 2);
+    // residual half-block -> buffer: fp32 box (32 rows x 64 B, SWIZZLE_64B) or, for a split residual, the hi and lo bf16 boxes
+    // (32 rows x 32 B each, unswizzled, at +0 and +1024)
+    auto load_res = [&](uint32_t dst, uint32_t bar, int n) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2048u) : "memory");
+        if (p.res_split) {
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmR)), "r"(bar), "r"(n), "r"(m_base) : "memory");
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                         ::"r"(dst + 1024u), "l"(reinterpret_cast<uint64_t>(tmR)), "r"(bar), "r"(p.ldr + n), "r"(m_base) : "memory");
+        } else {
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmR)), "r"(bar), "r"(n), "r"(m_base) : "memory");
+        }
+    };
     if (rows_ok && has_res && lane == 0) {
         // residual of half-block 0, issued while this tile's main loop may still be running; buffer 0 was last read by the
         // bulk store two groups back
         asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        tma_load_2d_s(buf_u32, tmR, bar_u32, ncol0, m_base, 2048);
+        load_res(buf_u32, bar_u32, ncol0);
     }
     mbar_wait(tmem_full_bar, tmem_full_parity);
     tc_fence_after();
@@ -587,7 +595,7 @@ __device__ __forceinline__ void epilogue_tile_tma_f32(const TcParams& p, const C
             if (has_res && j + 1 < NHB) {
                 // the other buffer was read by the most recent bulk store: wait for that read, then prefetch the next residual
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                tma_load_2d_s(buf_u32 + (uint32_t)(b ^ 1) * 2048u, tmR, bar_u32 + (uint32_t)(b ^ 1) * 8u, n + 16, m_base, 2048);
+                load_res(buf_u32 + (uint32_t)(b ^ 1) * 2048u, bar_u32 + (uint32_t)(b ^ 1) * 8u, n + 16);
             } else {
                 asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // this buffer's previous store (two groups back) is done reading
             }
@@ -598,11 +606,28 @@ __device__ __forceinline__ void epilogue_tile_tma_f32(const TcParams& p, const C
         if (has_res) {
             mbar_wait_s(bar_u32 + (uint32_t)b * 8u, (phases >> b) & 1u);
             phases ^= (1u << b);
+            if (p.res_split) {
+                // x = hi + lo (16 significant bits): this lane's 16 columns = 32 B of the hi box and 32 B of the lo box
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float r0, r1, r2, r3;
-                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r0), "=f"(r1), "=f"(r2), "=f"(r3) : "r"(rowa + (((uint32_t)c ^ sw) << 4)) : "memory");
-                f[4 * c] += r0; f[4 * c + 1] += r1; f[4 * c + 2] += r2; f[4 * c + 3] += r3;
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(h0), "=r"(h1), "=r"(h2), "=r"(h3) : "r"(buf + (uint32_t)lane * 32u + (uint32_t)c * 16u) : "memory");
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(l0), "=r"(l1), "=r"(l2), "=r"(l3) : "r"(buf + 1024u + (uint32_t)lane * 32u + (uint32_t)c * 16u) : "memory");
+                    const uint32_t hw[4] = {h0, h1, h2, h3}, lw[4] = {l0, l1, l2, l3};
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        f[8 * c + 2 * w] += __uint_as_float(hw[w] << 16) + __uint_as_float(lw[w] << 16);
+                        f[8 * c + 2 * w + 1] += __uint_as_float(hw[w] & 0xffff0000u) + __uint_as_float(lw[w] & 0xffff0000u);
+                    }
+                }
+                __syncwarp();  // the fp32 rows written below overlap OTHER lanes' hi / lo rows: everyone reads first
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float r0, r1, r2, r3;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r0), "=f"(r1), "=f"(r2), "=f"(r3) : "r"(rowa + (((uint32_t)c ^ sw) << 4)) : "memory");
+                    f[4 * c] += r0; f[4 * c + 1] += r1; f[4 * c + 2] += r2; f[4 * c + 3] += r3;
+                }
             }
         }
 #pragma unroll
@@ -1276,6 +1301,13 @@ extern "C" int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp
         if (e && !strcmp(e, "32x6")) variant = 1;
         if (e && !strcmp(e, "64x3")) variant = 2;
     }
+    // res_mod == -1: `residual` is a bf16 (hi|lo) split tensor [M, 2*ldr] (what the LayerNorm kernel writes), x = hi + lo
+    const int res_split = (residual && res_mod == -1) ? 1 : 0;
+    if (res_split) {
+        res_mod = 0;
+        AM_REQUIRE(variant == 3 && (ldr % 8) == 0 && (reinterpret_cast<uintptr_t>(residual) & 15u) == 0, AM_EINVAL,
+                   "am_linear_tc: split residual needs ldr % 8 == 0 and 16-byte alignment");
+    }
     if (variant == 3) {
         // tile width: 256 when that still gives every SM >= ~2 tiles, else 128 (more, smaller tiles)
         const int mt = cdiv(M, BM);
@@ -1294,7 +1326,7 @@ extern "C" int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp
         CUtensorMap tmA, tmB;
         AM_REQUIRE(make_map(&tmA, A2, (uint64_t)M, (uint64_t)2 * Kp, 32, BM), AM_ELAUNCH, "am_linear_tc: cuTensorMapEncodeTiled(A) failed");
         AM_REQUIRE(make_map(&tmB, W2, (uint64_t)N, (uint64_t)2 * Kp, 32, bn), AM_ELAUNCH, "am_linear_tc: cuTensorMapEncodeTiled(W) failed");
-        TcParams p{M, N, Kp, bias, act, residual, ldr, res_mod, Y, ldy, yin_g, yout_g, y_off, reinterpret_cast<__nv_bfloat16*>(Y2), Np2, 0, g_tc_dbg};
+        TcParams p{M, N, Kp, bias, act, residual, ldr, res_mod, Y, ldy, yin_g, yout_g, y_off, reinterpret_cast<__nv_bfloat16*>(Y2), Np2, 0, g_tc_dbg, res_split};
         p.vecY = Y && (reinterpret_cast<uintptr_t>(Y) & 15u) == 0 && (ldy % 4 == 0);
         const int grid = total < AM_NUM_SMS ? total : AM_NUM_SMS;
         cudaStream_t st = as_stream(stream);
@@ -1394,7 +1426,7 @@ extern "C" int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp
                            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) mode = 3;
         }
         if (plain && Y && !Y2 && (a15 == AM_ACT_NONE || a15 == AM_ACT_GELU) && (ldy % 4) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15u) == 0 &&
-            (!residual || ((ldr % 4) == 0 && (reinterpret_cast<uintptr_t>(residual) & 15u) == 0))) mode = 2;
+            (!residual || res_split || ((ldr % 4) == 0 && (reinterpret_cast<uintptr_t>(residual) & 15u) == 0))) mode = 2;
         CUtensorMap tmR = tmA;  // placeholder unless MODE 4 reads a residual
         if (mode == 2 && !lsu) {
             // fp32 tensor maps: Y [M, ldy] and residual [M, ldr], box 16 cols x 32 rows (64-byte rows), SWIZZLE_64B
@@ -1407,8 +1439,17 @@ extern "C" int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp
                 return enc && enc(mp, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
             };
-            if (f32map(&tmY, Y, ldy) && (!residual || f32map(&tmR, residual, ldr))) mode = 4;
+            auto splitmap = [&](CUtensorMap* mp) {  // bf16 [M, 2*ldr], box 16 cols x 32 rows (32-byte rows), no swizzle
+                cuuint64_t gdim[2] = {(cuuint64_t)2 * ldr, (cuuint64_t)M};
+                cuuint64_t gstr[1] = {(cuuint64_t)2 * ldr * 2};
+                cuuint32_t box[2] = {16, 32};
+                cuuint32_t estr[2] = {1, 1};
+                return enc && enc(mp, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<float*>(residual), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            };
+            if (f32map(&tmY, Y, ldy) && (!residual || (res_split ? splitmap(&tmR) : f32map(&tmR, residual, ldr)))) mode = 4;
         }
+        AM_REQUIRE(!res_split || mode == 4, AM_EINVAL, "am_linear_tc: a split residual is only supported by the TMA fp32 epilogue (plain layout, fp32 Y)");
         // MODE 5: row-mapped / broadcast-residual outputs with 16-byte rows (motion_adapter)
         if (mode == 0 && (yin_g > 0 || res_mod > 0) && (N % bn) == 0 && !(act & AM_ACT_AFTER_RES) && (a15 == AM_ACT_NONE || a15 == AM_ACT_GELU) &&
             (!bias || (reinterpret_cast<uintptr_t>(bias) & 15u) == 0) &&
@@ -1443,7 +1484,7 @@ extern "C" int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp
     CUtensorMap tmA, tmB;
     AM_REQUIRE(make_map(&tmA, A2, (uint64_t)M, (uint64_t)2 * Kp, BKsel), AM_ELAUNCH, "am_linear_tc: cuTensorMapEncodeTiled(A) failed");
     AM_REQUIRE(make_map(&tmB, W2, (uint64_t)N, (uint64_t)2 * Kp, BKsel), AM_ELAUNCH, "am_linear_tc: cuTensorMapEncodeTiled(W) failed");
-    TcParams p{M, N, Kp, bias, act, residual, ldr, res_mod, Y, ldy, yin_g, yout_g, y_off, reinterpret_cast<__nv_bfloat16*>(Y2), Np2, 0, g_tc_dbg};
+    TcParams p{M, N, Kp, bias, act, residual, ldr, res_mod, Y, ldy, yin_g, yout_g, y_off, reinterpret_cast<__nv_bfloat16*>(Y2), Np2, 0, g_tc_dbg, 0};
     p.vecY = Y && (reinterpret_cast<uintptr_t>(Y) & 15u) == 0 && (ldy % 4 == 0);
     dim3 grid(cdiv(N, BN), cdiv(M, BM));
     cudaStream_t st = as_stream(stream);
