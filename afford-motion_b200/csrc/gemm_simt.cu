@@ -257,6 +257,14 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) 
 
 }  // namespace
 
+int am_rowgemm_fwd_(const float* X, int ldx, const float* W, int ldw, int transW, float* Y, int ldy, int M, int N, int K, const float* bias,
+                    int act, const float* residual, int ldr, cudaStream_t st);
+static inline bool rowgemm_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("AMB200_ROWGEMM"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on != 0;
+}
+
 static int linear_f32_launch(const float* X, int ldx, const float* W, int ldw, float* Y, int ldy, int M, int N, int K, const float* bias,
                              int act, const float* residual, int ldr, int res_mod, int xin_g, int xout_g, int x_off, int yin_g,
                              int yout_g, int y_off, int nbatch, int64_t xb, int64_t wb, int64_t yb, int64_t bb, am_stream_t stream) {
@@ -269,6 +277,12 @@ static int linear_f32_launch(const float* X, int ldx, const float* W, int ldw, f
     p.vecA = al16(X) && (ldx % 4 == 0);
     p.vecB = al16(W) && (ldw % 4 == 0);
     p.vecY = al16(Y) && (ldy % 4 == 0);
+    // tall-skinny (N <= 32, many rows: per-neighbour MLPs of the Point-Transformer encoder): one thread per row (csrc/rowgemm.cu)
+    if (nbatch == 1 && xin_g == 0 && yin_g == 0 && res_mod == 0 && rowgemm_enabled() &&
+        am_rowgemm_fwd_(X, ldx, W, ldw, 0, Y, ldy, M, N, K, bias, act, residual, ldr, as_stream(stream))) {
+        AM_LAUNCH_CHECK("linear_f32");
+        return AM_OK;
+    }
     // small M (latent tokens): column-parallel kernel when the tiled one would launch only a handful of CTAs
     const size_t sm_smem = sizeof(float) * SM_ROWS * (size_t)((K + 3) & ~3);
     if (M <= 128 && (int64_t)cdiv(M, 64) * cdiv(N, 64) < 32 && sm_smem <= 48 * 1024) {

@@ -446,10 +446,23 @@ __global__ void masked_mse_bwd_kernel(const float* __restrict__ x0, const float*
 
 #define ST as_stream(stream)
 
+int am_rowgemm_fwd_(const float* X, int ldx, const float* W, int ldw, int transW, float* Y, int ldy, int M, int N, int K, const float* bias,
+                    int act, const float* residual, int ldr, cudaStream_t st);
+int am_rowgemm_dw_(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int R, int P, int Q, cudaStream_t st);
 extern "C" int am_gemm_f32(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb, float beta,
                            float* C, int ldc, int batch, int bdiv, int64_t sA1, int64_t sA2, int64_t sB1, int64_t sB2, int64_t sC1, int64_t sC2,
                            am_stream_t stream) {
     AM_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && batch > 0 && bdiv > 0, AM_EINVAL, "am_gemm_f32: bad args");
+    // tall-skinny shapes of the Point-Transformer encoder's backward (csrc/rowgemm.cu): dX = dY W with <= 32 input features,
+    // dW = dY^T X with min(out, in) <= 32 — the 64x64 tiles below are 75-97 % padding there
+    {
+        static int rg = -1;
+        if (rg < 0) { const char* e = getenv("AMB200_ROWGEMM"); rg = (e && e[0] == '0') ? 0 : 1; }
+        if (rg && batch == 1 && alpha == 1.f && beta == 0.f && !transB) {
+            if (!transA && am_rowgemm_fwd_(A, lda, B, ldb, 1, C, ldc, M, N, K, nullptr, 0, nullptr, 0, ST)) { AM_LAUNCH_CHECK("gemm_f32"); return AM_OK; }
+            if (transA && am_rowgemm_dw_(A, lda, B, ldb, C, ldc, K, M, N, ST)) { AM_LAUNCH_CHECK("gemm_f32"); return AM_OK; }
+        }
+    }
     GemmG g{A, B, C, M, N, K, lda, ldb, ldc, transA, transB, alpha, beta, bdiv, sA1, sA2, sB1, sB2, sC1, sC2, 1, K};
     dim3 grid(cdiv(N, 64), cdiv(M, 64), batch);
     // split-K for deep reductions with few output tiles (weight gradients dW = dY^T X: K = rows of the batch)
