@@ -87,7 +87,23 @@ rowgemm_dw_kernel(const float* __restrict__ A, int lda, const float* __restrict_
     for (int i = 0; i < NP; ++i) acc[i] = 0.f;
     const int r0 = blockIdx.x * rows_per_cta, r1 = min(R, r0 + rows_per_cta);
     if (t < wide) {
-        for (int r = r0 + ty; r < r1; r += NY) {
+        // four rows in flight per thread: the loop is pure load latency otherwise (one coalesced + NP broadcast loads per row)
+        int r = r0 + ty;
+        for (; r + 3 * NY < r1; r += 4 * NY) {
+            float wv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) wv[u] = Wd[(int64_t)(r + u * NY) * ldw + t];
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                if (i < narrow) {
+                    float a = acc[i];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) a = fmaf(__ldg(Nr + (int64_t)(r + u * NY) * ldn + i), wv[u], a);
+                    acc[i] = a;
+                }
+            }
+        }
+        for (; r < r1; r += NY) {
             const float wv = Wd[(int64_t)r * ldw + t];
             const float* nr = Nr + (int64_t)r * ldn;
 #pragma unroll
@@ -136,8 +152,8 @@ int am_rowgemm_dw_(const float* A, int lda, const float* B, int ldb, float* C, i
     const int WT = ((wide + 31) / 32) * 32, NY = 256 / WT > 0 ? 256 / WT : 1;
     const size_t smem = sizeof(float) * (size_t)NY * NP * WT;
     if (smem > 48 * 1024) return 0;
-    int ctas = cdiv(R, 2048);
-    if (ctas > 2 * AM_NUM_SMS) ctas = 2 * AM_NUM_SMS;
+    int ctas = cdiv(R, 256);  // >= 256 rows per CTA; up to 4 CTAs per SM so the row loop's load latency overlaps across CTAs
+    if (ctas > 4 * AM_NUM_SMS) ctas = 4 * AM_NUM_SMS;
     const int rows_per_cta = cdiv(R, ctas);
     cudaMemsetAsync(C, 0, sizeof(float) * ((size_t)(P - 1) * ldc + Q), st);
     dim3 grid(cdiv(R, rows_per_cta)), block(WT, NY);
