@@ -8,8 +8,17 @@
 // 1.9e-2 on CMDM and kind::tf32 truncates to 10 mantissa bits (~2.4e-3).  3 bf16 MMAs per product
 // cost 3/2.25 PF = 1.33 us/TFLOP — still 10x the fp32 SIMT pipe.
 //
-// Kernel shape (one 128x128 output tile per CTA, 2 CTAs co-resident per SM so one CTA's epilogue overlaps the
-// other's main loop):
+// Kernels in this file (am_linear_tc picks one per call):
+//   gemm_tc_2sm_kernel        DEFAULT.  Persistent CTA pairs, tcgen05.mma.cta_group::2 (UMMA M = 256): each SM of the pair holds
+//                             its own 128 A rows and HALF of the W tile (BK = 64, SWIZZLE_128B rows; BK = 32 when Kp % 64 != 0),
+//                             256- or 128-wide tiles with the last partial round cut into half-width items, accumulators
+//                             double-buffered in TMEM, 8 epilogue warps.  Epilogue modes: 3 = bias(+GELU) -> bf16 (hi|lo) via TMA
+//                             store, 4 = bias(+GELU)(+ fp32 or bf16-pair residual via TMA load) -> fp32 via TMA store, 5 = token row
+//                             map / broadcast residual with 16-byte LSU accesses, 0 = general (any N, any map), 1 / 2 = LSU
+//                             variants of 3 / 4 (AMB200_TC_EPI=lsu).
+//   gemm_tc_persistent_kernel 1-SM persistent kernel (small problems: fewer than 16 tile pairs; AMB200_TC_2SM=0)
+//   gemm_tc_cluster_kernel    1-SM kernel with 2-CTA W multicast (kept for A/B runs: measured no faster)
+//   gemm_tc_kernel            legacy one-128x128-tile-per-CTA kernels (AMB200_TC_VARIANT=32x3|32x6|64x3), described below:
 //   warp 0      : TMA producer  — per K-block of 32 loads the FOUR 128x32 sub-tiles {A_hi, A_lo, W_hi, W_lo}
 //                 (SWIZZLE_64B, 8 KB each) exactly once into a 3-stage mbarrier ring (each sub-tile feeds 2 MMAs)
 //   warp 1      : MMA issuer    — one thread issues 6 x tcgen05.mma (M128 N128 K16, kind::f16 bf16->f32) per stage,
