@@ -322,7 +322,7 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "denoise-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "fp32", "data": "synthetic",
+                "dtype": "fp32 (tensor-core GEMMs as 3-term bf16 split with fp32 accumulation; elementwise / softmax / LayerNorm fp32)", "data": "synthetic",
                 "config": {"workload": f"CMDM {nd}-step DDPM sampling, batch=32 per GPU, T=196, D=263, N=8192 (configs[1]); "
                                        "bench step = one full sampling job incl. conditioning encode",
                            "global_batch": B * world, "denoise_steps_per_job": nd, "parallelism": f"batch-sharded x{world}, no collective",

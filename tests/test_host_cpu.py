@@ -126,3 +126,23 @@ def test_adamw_oracle_matches_torch_optim():
         for i in range(2):
             adamw_step(mine[i], grads[i], m[i], v[i], step, lr=3e-3, weight_decay=0.02)
             assert torch.allclose(mine[i], params[i].data, rtol=0, atol=1e-7), (step, i)
+
+
+def test_fused_adamw_and_scene_model_host_behaviour():
+    """Host-side contracts that need no GPU: the fused optimiser refuses CPU parameters loudly (no CPU fallback), the scene-model
+    factory builds the reference's PointTransformerSeg tree (functions.py:96-126) frozen, and rejects the ablation-only encoder."""
+    from amb200.lib import AmbError
+    from amb200.optim import FusedAdamW
+    from amb200.dist import allreduce_flat_
+    from models.functions import load_scene_model
+    with pytest.raises(AmbError):
+        FusedAdamW([torch.nn.Parameter(torch.zeros(4))], lr=1e-3)
+    assert allreduce_flat_([torch.ones(3)]) == 1  # no process group: no-op, world size 1
+    seg = load_scene_model("PointTransformerSeg", 3, 1024, None, freeze=True)
+    keys = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "state_keys.json")))["PointTransformerSeg_c3"]
+    assert {k: list(v.shape) for k, v in seg.state_dict().items()} == keys
+    assert not seg.training and not any(p.requires_grad for p in seg.parameters()) and seg.num_groups == 4
+    with pytest.raises(NotImplementedError):
+        load_scene_model("PointTransformerEnc", 3, 1024)
+    with pytest.raises(RuntimeError):  # executing it needs the CUDA library + a GPU: CPU tensors are refused, not emulated
+        seg((torch.zeros(1, 1024, 3), None))
