@@ -200,12 +200,12 @@ int am_linear_skinny(const float* X1, int ldx1, int K1, const float* X2, int ldx
  * (Y2 [rows, 2*Np2], Np2 % 32 == 0, padding columns zeroed) for the next GEMM.  Row map as in am_linear_f32,
  * plus: a mapped row outside [0, yout_g) is skipped (lets a GEMM over all [B,S] tokens emit only motion rows).
  * Replaces the cuBLAS GEMMs behind nn.Linear / in_proj / out_proj / linear1 / linear2 (models/cmdm.py:66-77,195)
- * and the decoder MLP of the Perceiver (models/cdm.py:186, modules.py:651-661). */
+ * and the decoder MLP of the Perceiver (models/cdm.py:186, modules.py:651-661).
+ * res_mod == -1: `residual` is itself a bf16 (hi|lo) split tensor [M, 2*ldr] (e.g. the previous am_layernorm's Y2), added as
+ * hi + lo; supported for the plain fp32-output layout (no row map), 16-byte aligned, ldr % 8 == 0. */
 int am_split_bf16(const float* X, int ldx, void* X2, int Kp, int M, int K, am_stream_t stream);
 /* bf16 (hi|lo) of the TRANSPOSE: X [M,K] fp32 -> XT2 [K, 2*Mp] (Mp % 32 == 0, zero padded): operands of the backward GEMMs
- * dX = dY W (W^T as the K-major operand) and dW = dY^T X (both operands K-major along the batch rows)  * res_mod == -1: `residual` is itself a bf16 (hi|lo) split tensor [M, 2*ldr] (e.g. the previous am_layernorm's Y2), added as
- * hi + lo; supported for the plain fp32-output layout (no row map), 16-byte aligned, ldr % 8 == 0.
- */
+ * dX = dY W (W^T as the K-major operand) and dW = dY^T X (both operands K-major along the batch rows) */
 int am_transpose_split_bf16(const float* X, int ldx, void* XT2, int Mp, int M, int K, am_stream_t stream);
 int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp, const float* bias, int act,
                  const float* residual, int ldr, int res_mod, float* Y, int ldy, int yin_g, int yout_g, int y_off,
