@@ -10,8 +10,9 @@ from models.base import create_model_and_diffusion
 from models.functions import set_text_feature_provider
 dev = torch.device("cuda:0")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+BASE = int(sys.argv[2]) if len(sys.argv) > 2 else 500   # base diffusion steps: 500 (reference CDM scripts) or 1000 (stride 10)
 N = 8192
-model, diff = create_model_and_diffusion(full_cfg(cdm_model_cfg(N), steps=500, timestep_respacing="ddim100"), device=dev)
+model, diff = create_model_and_diffusion(full_cfg(cdm_model_cfg(N), steps=BASE, timestep_respacing="ddim100"), device=dev)
 model.load_state_dict(synth.fill_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed=0), strict=False)
 model.to(dev).eval()
 txt = synth.text_features(B, seed=3).to(dev)
@@ -36,4 +37,4 @@ for rep in range(2):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     s = diff.ddim_sample_loop(model, (B, N, 6), clip_denoised=False, model_kwargs=kw, eta=0.0)
     torch.cuda.synchronize(); t1 = time.perf_counter()
-    print(f"ddim100 job (B={B}): {1e3*(t1-t0):.1f} ms -> {100/(t1-t0):.1f} denoise-steps/s, {B/(t1-t0):.1f} affordance maps/s, finite={bool(torch.isfinite(s).all())}")
+    print(f"ddim100-of-{BASE} job (B={B}): {1e3*(t1-t0):.1f} ms -> {100/(t1-t0):.1f} denoise-steps/s, {B/(t1-t0):.1f} affordance maps/s, finite={bool(torch.isfinite(s).all())}")
