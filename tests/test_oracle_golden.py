@@ -180,3 +180,47 @@ def test_cdm_with_scene_model_oracle_matches_reference(golden_dir):
     out = cdm_ref.cdm_forward(sd, x, torch.from_numpy(g["t"]), txt, xyz, point_feat=pf)
     err = np.abs(out.numpy() - g["cdm_scene_out"]).max()
     assert err < TOL, err
+
+
+def test_pointops_oracle_properties_on_ragged_random_segments():
+    """The pointops_cuda boundary is unpinned (source absent), so its restatement is cross-checked three ways on ragged batches
+    with exact duplicates (ties -> lowest index): C oracle == independent numpy statement, FPS picks are unique per segment and
+    start at the segment's first row, kNN distances are sorted and every neighbour stays inside the query's segment."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=25, deadline=None)
+    @given(st.lists(st.integers(min_value=1, max_value=70), min_size=1, max_size=4), st.integers(min_value=1, max_value=16),
+           st.integers(min_value=0, max_value=2 ** 31 - 1))
+    def check(lens, k, seed):
+        rng = np.random.default_rng(seed)
+        n = sum(lens)
+        xyz = rng.uniform(-2, 2, size=(n, 3)).astype(np.float32)
+        dup = rng.integers(0, n, size=max(1, n // 8))
+        xyz[dup] = xyz[rng.integers(0, n, size=len(dup))]          # exact duplicates: ties in both FPS and kNN
+        o = np.cumsum(lens).astype(np.int32)
+        mlens = [max(1, L // 4) for L in lens]
+        no = np.cumsum(mlens).astype(np.int32)
+        t = torch.from_numpy
+        fidx = pointops_ref.furthestsampling(t(xyz), t(o), t(no)).numpy()
+        assert (fidx == pointops_ref.fps_numpy(xyz, o.tolist(), no.tolist())).all()
+        s_n = s_m = 0
+        for e_n, e_m in zip(o.tolist(), no.tolist()):
+            seg = fidx[s_m:e_m]
+            assert seg[0] == s_n and ((seg >= s_n) & (seg < e_n)).all()
+            if len(set(map(tuple, xyz[s_n:e_n]))) >= len(seg):     # enough distinct points: no index is picked twice
+                assert len(set(seg.tolist())) == len(seg)
+            s_n, s_m = e_n, e_m
+        q = xyz[fidx]
+        kidx, kd = pointops_ref.knnquery(k, t(xyz), t(q), t(o), t(no))
+        i2, d2 = pointops_ref.knn_numpy(k, xyz, q, o.tolist(), no.tolist())
+        assert (kidx.numpy() == i2).all() and np.allclose(kd.numpy() ** 2, d2, rtol=1e-5, atol=1e-7)
+        s_n = s_m = 0
+        for e_n, e_m in zip(o.tolist(), no.tolist()):
+            have = min(k, e_n - s_n)
+            blk = kidx.numpy()[s_m:e_m, :have]
+            assert ((blk >= s_n) & (blk < e_n)).all()
+            assert (np.diff(kd.numpy()[s_m:e_m, :have], axis=1) >= 0).all()
+            assert (kidx.numpy()[s_m:e_m, have:] == 0).all()      # fewer candidates than k: slots keep the zero fill
+            assert (kd.numpy()[s_m:e_m, 0] == 0).all()            # every query is one of the segment's own points
+            s_n, s_m = e_n, e_m
+    check()
