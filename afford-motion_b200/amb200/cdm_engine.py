@@ -15,6 +15,7 @@ from typing import Dict, Optional
 import torch
 
 from . import ops
+from .cdm_fold import fold_constants
 from .pack import c, params_version
 
 R = 16  # (head, latent) rows
@@ -40,6 +41,9 @@ class CDMEngine:
         self.w: Dict[str, torch.Tensor] = {}
         self._ws = {}
         self.gemm = os.environ.get("AMB200_GEMM", "tc")  # tcgen05 (default) or fp32 SIMT for the per-point MLP GEMM
+        # point path: "collapsed" (default when cin == 9: rank-collapsed kernels of csrc/perceiver_tc.cu) or "general"
+        self.point_path = os.environ.get("AMB200_CDM_POINTS", "collapsed")
+        self.K = None
 
     def refresh(self):
         v = params_version(self.m)
@@ -136,6 +140,10 @@ class CDMEngine:
         w["head_w"] = torch.cat([Wc, Wc @ _d(dm_[3].weight)], dim=1).float().contiguous()
         w["head_b"] = (Wc @ _d(dm_[3].bias) + bc).float().contiguous()
         self.out_dim = m.contact_layer.out_features
+        # rank-collapsed point path (H3D configs: u = cat(x_t [6], xyz [3]); see amb200/cdm_fold.py)
+        self.K = None
+        if cm.encoder_adapter.in_features == 9 and self.out_dim == 6 and self.He == 8 and self.Hd == 8:
+            self.K = {k: (t.to(dev) if torch.is_tensor(t) else t) for k, t in fold_constants(m).items()}
         self.w = w
         self._version = v
 
@@ -167,6 +175,31 @@ class CDMEngine:
             self._ws[key] = ws
         return ws
 
+    def workspace_collapsed(self, B, N, dev):
+        key = ("c", B, N, str(dev))
+        ws = self._ws.get(key)
+        if ws is None:
+            DL, C = self.DL, self.C
+            d = self.K["dims"]
+            AEW, NS = d["KU"] + 2, d["NS"]
+            e = lambda *s: torch.empty(*s, device=dev)
+            nchunk = 1
+            while B * nchunk < 2 * 148 and N // (nchunk * 2) >= 256:
+                nchunk *= 2
+            ws = dict(L0=e(B, 2, DL), LN=e(2 * B, DL), Q=e(2 * B, DL), AE=e(B, R, AEW), PART=e(B, nchunk, R, AEW), Z=e(B, R, C),
+                      AO=e(2 * B, DL), La=e(2 * B, DL), Lb=e(2 * B, DL), Hh=e(2 * B, DL), QKV=e(2 * B, 3 * DL), KV=e(2 * B, 2 * C),
+                      AQ=e(B, R, AEW), UU=e(B, R, NS), PB=torch.zeros(B, 768, device=dev),
+                      BLOB=torch.zeros(B, 32768, dtype=torch.uint8, device=dev), nchunk=nchunk, cond_id=None)
+            self._ws[key] = ws
+        return ws
+
+    def is_collapsed(self, cond) -> bool:
+        return self.K is not None and cond.point_feat is None and self.point_path == "collapsed"
+
+    def workspace_for(self, cond):
+        dev = cond.xyz.device
+        return self.workspace_collapsed(cond.B, cond.N, dev) if self.is_collapsed(cond) else self.workspace(cond.B, cond.N, dev)
+
     @torch.no_grad()
     def forward(self, x, t_dev, t_stride, cond: CDMCondition, out=None, time_table=None):
         """x [B,N,cx] fp32, t_dev int32 device -> x0_hat [B,N,contact_dim]."""
@@ -178,7 +211,8 @@ class CDMEngine:
         if cond.point_feat is not None:  # cdm.py:167-168
             x = torch.cat([x, cond.point_feat], dim=-1).contiguous()
             cx = x.shape[-1]
-        ws = self.workspace(B, N, dev)
+        collapsed = self.is_collapsed(cond)
+        ws = self.workspace_for(cond)
         if ws["cond_id"] is not cond:
             ws["L0"][:, 0, :].copy_(cond.text_latent)
             ws["cond_id"] = cond
@@ -189,12 +223,20 @@ class CDMEngine:
         ops.layernorm(L0, w["e_qn_g"], w["e_qn_b"], ws["LN"], M2, DL)
         ops.linear(ws["LN"], w["e_q_w"], ws["Q"], M2, DL, DL, bias=w["e_q_b"])
         hd = DL // He
-        # qf[b, 2h+l, :C] = Wk_h^T q_{h,l} ; [.., C] = q_{h,l}.bk_h      (all heads in one batched launch)
-        ops.linear_batched(ws["Q"], w["e_kfold"], ws["QF"], M2, C + 1, hd, He, hd, (C + 1) * hd, 2 * (C + 4), ldx=DL, ldy=C + 4,
-                           ymap=(2, R, 0))
-        ops.cdm_encoder_partial(x, cond.xyz, w["ea_w"], w["ea_b"], w["e_kvn_g"], w["e_kvn_b"], ws["QF"], C + 4, ws["PART"], B, N, cx,
-                                ws["nchunk"])
-        ops.cdm_encoder_combine(ws["PART"], ws["Z"], B, ws["nchunk"])
+        if collapsed:
+            K = self.K
+            AEW = K["dims"]["KU"] + 2
+            # AE[b, 2h+l, :] = q_{h,l}^T [Wk_h diag(g) Ec | Wk_h beta + bk_h]      (all heads in one batched launch)
+            ops.linear_batched(ws["Q"], K["e_kfold"], ws["AE"], M2, AEW, hd, He, hd, AEW * hd, 2 * AEW, ldx=DL, ldy=AEW, ymap=(2, R, 0))
+            ops.cdm_enc_points(x, cond.xyz, K["e_chol"], ws["AE"], ws["PART"], B, N, ws["nchunk"])
+            ops.cdm_enc_expand(ws["PART"], K["e_ecg"], K["e_beta"], ws["Z"], B, ws["nchunk"])
+        else:
+            # qf[b, 2h+l, :C] = Wk_h^T q_{h,l} ; [.., C] = q_{h,l}.bk_h      (all heads in one batched launch)
+            ops.linear_batched(ws["Q"], w["e_kfold"], ws["QF"], M2, C + 1, hd, He, hd, (C + 1) * hd, 2 * (C + 4), ldx=DL, ldy=C + 4,
+                               ymap=(2, R, 0))
+            ops.cdm_encoder_partial(x, cond.xyz, w["ea_w"], w["ea_b"], w["e_kvn_g"], w["e_kvn_b"], ws["QF"], C + 4, ws["PART"], B, N, cx,
+                                    ws["nchunk"])
+            ops.cdm_encoder_combine(ws["PART"], ws["Z"], B, ws["nchunk"])
         # o_{h,l} = Wv_h z_{h,l} + bv_h
         ops.linear_batched(ws["Z"], w["e_v_w"], ws["AO"], M2, hd, C, He, 2 * C, hd * C, hd, bias=w["e_v_b"], bb=hd, ldy=DL, xmap=(2, R, 0))
         ops.linear(ws["AO"], w["e_o_w"], ws["La"], M2, DL, DL, bias=w["e_o_b"], residual=L0)  # residual on un-normalised L (:230)
@@ -216,6 +258,17 @@ class CDMEngine:
         ops.layernorm(cur, w["d_kvn_g"], w["d_kvn_b"], ws["LN"], M2, DL)
         ops.linear(ws["LN"], w["d_kv_w"], ws["KV"], M2, 2 * C, DL, bias=w["d_kv_b"])
         hdd = self.hdd
+        if out is None:
+            out = torch.empty(B, N, self.out_dim, device=dev)
+        if collapsed:
+            NS = K["dims"]["NS"]
+            ops.linear_batched(ws["KV"], K["d_qfold"], ws["AQ"], M2, AEW, hdd, Hd, hdd, AEW * hdd, 2 * AEW, ldx=2 * C, ldy=AEW,
+                               ymap=(2, R, 0))
+            ops.linear_batched(ws["KV"][:, C:], K["d_ostack"], ws["UU"], M2, NS, hdd, Hd, hdd, hdd, 2 * NS, ldx=2 * C, ldw=C, ldy=NS,
+                               ymap=(2, R, 0))
+            ops.cdm_dec_prep(ws["AQ"], ws["UU"], NS, K["d_g1uu"], K["d_mu"], K["d_hu"], ws["PB"], ws["BLOB"], B)
+            ops.cdm_dec_points_tc(x, cond.xyz, K["d_chol"], K["d_c1"], K["d_wg"], ws["PB"], ws["BLOB"], out, B, N)
+            return out
         ops.linear_batched(ws["KV"], w["d_qfold"], ws["KF"], M2, C + 1, hdd, Hd, hdd, (C + 1) * hdd, 2 * (C + 4), ldx=2 * C, ldy=C + 4,
                            ymap=(2, R, 0))
         ops.linear_batched(ws["KV"][:, C:], w["d_o_w"], ws["U"], M2, C, hdd, Hd, hdd, hdd, 2 * C, ldx=2 * C, ldw=C, ymap=(2, R, 0))
@@ -225,7 +278,5 @@ class CDMEngine:
             ops.linear_tc(ws["HN2"], w["d_m1_w2"], B * N, C, C, y=ws["Gm"], bias=w["d_m1_b"], act="gelu")
         else:
             ops.linear(ws["HN"], w["d_m1_w"], ws["Gm"], B * N, C, C, bias=w["d_m1_b"], act="gelu")
-        if out is None:
-            out = torch.empty(B, N, self.out_dim, device=dev)
         ops.linear_skinny(ws["H1"], C, ws["Gm"], C, w["head_w"], w["head_b"], out, B * N, self.out_dim)
         return out

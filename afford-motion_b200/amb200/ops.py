@@ -193,6 +193,28 @@ def cdm_decoder_point(x_t, xyz, wd, bd, lnq_g, lnq_b, kf, ldk, U, bo, lnm_g, lnm
              "am_cdm_decoder_point")
 
 
+def cdm_enc_points(x_t, xyz, chol, AE, part, B, N, nchunk):
+    _chk_cuda(x_t, xyz, part)
+    _l.check(_l.load().am_cdm_enc_points(_ptr(_f32c(x_t)), _ptr(_f32c(xyz)), _ptr(chol), _ptr(AE), _ptr(part), B, N, nchunk, _stream()),
+             "am_cdm_enc_points")
+
+
+def cdm_enc_expand(part, ecg, beta, z, B, nchunk):
+    _l.check(_l.load().am_cdm_enc_expand(_ptr(part), _ptr(ecg), _ptr(beta), _ptr(z), B, nchunk, _stream()), "am_cdm_enc_expand")
+
+
+def cdm_dec_prep(AQ, UU, NS, g1uu, mu, hu, PB, blob, B):
+    _l.check(_l.load().am_cdm_dec_prep(_ptr(AQ), _ptr(UU), NS, _ptr(g1uu), _ptr(mu), _ptr(hu), _ptr(PB), _ptr(blob), B, _stream()),
+             "am_cdm_dec_prep")
+
+
+def cdm_dec_points_tc(x_t, xyz, chol, c1, wg, PB, blob, out, B, N):
+    _chk_cuda(x_t, xyz, out)
+    _l.check(_l.load().am_cdm_dec_points_tc(_ptr(_f32c(x_t)), _ptr(_f32c(xyz)), _ptr(chol), _ptr(c1), _ptr(wg), _ptr(PB), _ptr(blob),
+                                           _ptr(_f32c(out)), B, N, _stream()), "am_cdm_dec_points_tc")
+    return out
+
+
 def linear_skinny(x1, K1, x2, K2, W, bias, y, M, N, ldx1=None, ldx2=None, ldy=None):
     _l.check(_l.load().am_linear_skinny(_ptr(x1), K1 if ldx1 is None else ldx1, K1, _ptr(x2), (K2 if ldx2 is None else ldx2), K2, _ptr(W),
                                        _ptr(bias), _ptr(y), N if ldy is None else ldy, M, N, _stream()), "am_linear_skinny")
@@ -284,5 +306,6 @@ def _wrap(name, fn):
 
 for _n in ("randn_", "p_sample_update", "ddim_update", "q_sample", "masked_mse", "add_i32", "linear", "linear_batched", "layernorm", "mha_fwd",
            "gather_time_token", "gather_rows", "furthestsampling", "knnquery", "pt_layer_fwd", "transition_down_fwd", "interpolation", "segment_mean",
-           "cdm_encoder_partial", "cdm_encoder_combine", "cdm_decoder_point", "linear_skinny", "split_bf16", "linear_tc", "mha_tc_fwd"):
+           "cdm_encoder_partial", "cdm_encoder_combine", "cdm_decoder_point", "cdm_enc_points", "cdm_enc_expand", "cdm_dec_prep",
+           "cdm_dec_points_tc", "linear_skinny", "split_bf16", "linear_tc", "mha_tc_fwd"):
     globals()[_n] = _wrap(_n, globals()[_n])

@@ -62,7 +62,17 @@ static inline cudaError_t am_launch(void (*kernel)(KArgs...), dim3 grid, dim3 bl
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
-#define AM_NUM_SMS 148
+// SM count of the current device (148 on B200), queried once per process instead of hard-coded
+static inline int am_num_sms() {
+    static int n = 0;
+    if (n <= 0) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
+        else return 148;
+    }
+    return n;
+}
+#define AM_NUM_SMS am_num_sms()
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

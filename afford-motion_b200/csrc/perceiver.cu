@@ -305,7 +305,7 @@ extern "C" int am_cdm_decoder_point(const float* x_t, const float* xyz, const fl
     if (rc) return rc;
     // ~2 waves of CTAs over the 148 SMs (4 CTAs of 8 warps resident per SM)
     int pts = 64;
-    while ((int64_t)cdiv(N, pts) * B > 148 * 8 && pts < 1024) pts *= 2;
+    while ((int64_t)cdiv(N, pts) * B > AM_NUM_SMS * 8 && pts < 1024) pts *= 2;
     am_launch(cdm_decoder_point_kernel, dim3(dim3(cdiv(N, pts), B)), dim3(PW * 32), smem, as_stream(stream), 1, x_t, xyz, wd, bd, lnq_g, lnq_b, kf, ldk, U, bo,
                                                                                           lnm_g, lnm_b, h1, hn, reinterpret_cast<__nv_bfloat16*>(hn2), N, cx, pts);
     AM_LAUNCH_CHECK("cdm_decoder_point");
@@ -318,7 +318,7 @@ extern "C" int am_linear_skinny(const float* X1, int ldx1, int K1, const float* 
     AM_REQUIRE((X2 != nullptr) == (K2 > 0), AM_EINVAL, "am_linear_skinny: X2/K2 mismatch");
     size_t smem = sizeof(float) * (size_t)N * (K1 + K2);
     AM_REQUIRE(smem <= 48 * 1024, AM_EINVAL, "am_linear_skinny: weight does not fit shared memory");
-    int grid = cdiv(M, 8) < 148 * 8 ? cdiv(M, 8) : 148 * 8;
+    int grid = cdiv(M, 8) < AM_NUM_SMS * 8 ? cdiv(M, 8) : AM_NUM_SMS * 8;
     am_launch(linear_skinny_kernel, dim3(grid), dim3(256), smem, as_stream(stream), 1, X1, ldx1, K1, X2, ldx2, K2, W, bias, Y, ldy, M, N);
     AM_LAUNCH_CHECK("linear_skinny");
     return AM_OK;

@@ -64,7 +64,7 @@ class CMDM(nn.Module):
         self.motion_layer = nn.Linear(self.latent_dim, self.motion_dim, bias=True)
 
         self._engine = None
-        self._cond_cache = (None, None)
+        self._cond_cache = None
 
     # ------------------------------------------------------------------ engine plumbing
     @property
@@ -74,19 +74,28 @@ class CMDM(nn.Module):
             self._engine = CMDMEngine(self)
         return self._engine
 
-    def _cond_key(self, kwargs):
-        def tk(t):
-            return None if t is None else (t.data_ptr(), t._version, tuple(t.shape))
-        return (tuple(kwargs["c_text"]), tk(kwargs["c_pc_xyz"]), tk(kwargs["c_pc_contact"]), tk(kwargs.get("x_mask")),
-                tk(kwargs.get("c_text_mask")), tk(kwargs.get("c_text_erase")), tk(kwargs.get("c_pc_mask")), tk(kwargs.get("c_pc_erase")),
-                self.engine._version)
+    _COND_TENSOR_KEYS = ("c_pc_xyz", "c_pc_contact", "x_mask", "c_text_mask", "c_text_erase", "c_pc_mask", "c_pc_erase")
 
-    def encode_condition(self, T, **kwargs):
-        """Step-invariant conditioning (text token, contact tokens, key mask); cached while the inputs are unchanged."""
+    def _cond_lookup(self, kwargs):
+        """Per-step `forward()` cache (the reference's loop calls the model with the SAME kwargs dict on every step, test.py:94-101).
+        Keyed on the identity of the input tensor OBJECTS, which the cache entry keeps alive (so an address can never be recycled
+        under it), plus their in-place-modification counters — never on data_ptr."""
+        ents = tuple(kwargs.get(k) for k in self._COND_TENSOR_KEYS)
+        sig = (tuple(kwargs["c_text"]), tuple(None if t is None else t._version for t in ents), self.engine._version)
+        c = self._cond_cache
+        if c is not None and c["sig"] == sig and all(a is b for a, b in zip(c["refs"], ents)):
+            return c["cond"], ents, sig
+        return None, ents, sig
+
+    def encode_condition(self, T, use_cache=True, **kwargs):
+        """Step-invariant conditioning (text token, contact tokens, key mask).  use_cache=False (sampler_begin: once per job)
+        always re-encodes."""
         self.engine.refresh()
-        key = self._cond_key(kwargs)
-        if self._cond_cache[0] == key:
-            return self._cond_cache[1]
+        ents = sig = None
+        if use_cache:
+            cond, ents, sig = self._cond_lookup(kwargs)
+            if cond is not None:
+                return cond
         dev = kwargs["c_pc_xyz"].device
         text = encode_text_clip(self.text_model, kwargs["c_text"], max_length=self.text_max_length, device=dev).detach().float()
         B = kwargs["c_pc_xyz"].shape[0]
@@ -96,7 +105,8 @@ class CMDM(nn.Module):
         cond = self.engine.encode_condition(text, kwargs["c_pc_xyz"], kwargs["c_pc_contact"], x_mask, T,
                                             c_text_mask=kwargs.get("c_text_mask"), c_text_erase=kwargs.get("c_text_erase"),
                                             c_pc_mask=kwargs.get("c_pc_mask"), c_pc_erase=kwargs.get("c_pc_erase"))
-        self._cond_cache = (key, cond)
+        if use_cache:
+            self._cond_cache = dict(sig=sig, refs=ents, cond=cond)
         return cond
 
     def forward(self, x, timesteps, **kwargs):
@@ -118,7 +128,7 @@ class CMDM(nn.Module):
         bound into the engine's persistent token buffer; the handle itself (re-indexed time-token table, key-padding buffer,
         loop plans with their captured CUDA graph) is PERSISTENT per (shape, timestep map, weight version), so later jobs of
         the same shape replay the first job's graph."""
-        cond = self.encode_condition(shape[1], **model_kwargs)
+        cond = self.encode_condition(shape[1], use_cache=False, **model_kwargs)  # once per job, never from a cache
         eng = self.engine
         key = (tuple(shape), tuple(timestep_map), eng._version, cond.key_pad is None, cond.G, str(cond.static_tokens.device))
         handles = self.__dict__.setdefault("_sampler_handles", {})

@@ -248,7 +248,7 @@ def main():
     kw_res = dict(c_text=host["texts"], c_pc_xyz=host["xyz"].to(dev), c_pc_contact=host["contact"].to(dev), x_mask=host["x_mask"].to(dev))
 
     def resident_once():
-        model._cond_cache = (None, None)  # every job re-encodes its conditioning (new batch semantics)
+        model._cond_cache = None  # every job re-encodes its conditioning (new batch semantics)
         job_resident(kw_res)
 
     clocks = ClockSampler(local)

@@ -192,6 +192,36 @@ int am_cdm_decoder_point(const float* x_t, const float* xyz, const float* wd, co
 int am_linear_skinny(const float* X1, int ldx1, int K1, const float* X2, int ldx2, int K2, const float* W,
                      const float* bias, float* Y, int ldy, int M, int N, am_stream_t stream);
 
+/* ------------------------------------------------------------------ CDM Perceiver, rank-collapsed point path (cin = 9)
+ * models/cdm.py:155-188,511 + models/modules.py:324-381,504-541,651-661 with u = cat(x_t [6], xyz [3]) (cdm.py:167-171, H3D
+ * configs: no scene features).  Every per-point quantity is a function of the 10-vector [u;1] (derivation and the weights-only
+ * constants: afford-motion_b200/amb200/cdm_fold.py), so enc_kv / K / V / dq / h1 / LN(h1) / GELU activations never exist in
+ * HBM: 36 B/point read by each of the two point kernels, 24 B/point written.  The general-cin kernels above remain the path
+ * for scene-feature inputs (cin = 41).
+ *
+ * am_cdm_enc_points : encoder cross-attention (cdm.py:174-180).  chol = packed upper Cholesky factor [55] of Ec^T Ec / 256
+ *   (LayerNorm variance as a sum of squares); AE [B,16,12]: row r = head*2 + latent, columns 0..9 = q^T Wk_h diag(g) Ec,
+ *   column 10 = q^T (Wk_h beta + bk_h).  score_r(j) = rstd_j * AE[r,:10].[u_j;1] + AE[r,10]; flash partials
+ *   part [B,nchunk,16,12] = (sum_j p_j rstd_j [u_j;1] (10), running max, sum).
+ * am_cdm_enc_expand : combines the partials and expands z[b,r,:] = diag(g) Ec w_r + beta  ([B,16,256], the softmax-weighted
+ *   mean of LN_kv(enc_kv) rows; the V projection is applied afterwards on 16 rows).  ecg [256,10], beta [256]. */
+int am_cdm_enc_points(const float* x_t, const float* xyz, const float* chol, const float* AE, float* part, int B, int N,
+                      int nchunk, am_stream_t stream);
+int am_cdm_enc_expand(const float* part, const float* ecg, const float* beta, float* z, int B, int nchunk,
+                      am_stream_t stream);
+/* am_cdm_dec_prep : per-sample operands of the decoder point kernel from the latent side (cdm.py:184-186).  AQ [B,16,12] as AE
+ *   (decoder q_proj folded against the 2 K tokens); UU [B,16,NS] = o_proj stack applied to the V tokens: columns [0,256) centred
+ *   U_r, [256,512) U_r W1g^T, [512,522) G1 cross block, [522,528) U_r Wc^T.  Writes PB [B,768] fp32 (scores, packed 26x26
+ *   LayerNorm Gram matrix, head coefficients) and blob [B, 32 KB]: bf16 (hi | lo) [256 x 32] K-major SWIZZLE_64B image of
+ *   M = W1 diag(g_m) Hc, the B operand of the per-point GEMM.
+ * am_cdm_dec_points_tc : decoder cross-attention + MLP + contact_layer (cdm.py:186-188,511) per 128-point tile:
+ *   z = [u;1;p] (26), D[128,256] = Z[128,32] M^T on tcgen05 (3-term bf16 split, fp32 TMEM accumulation),
+ *   out = HP z + Wg gelu(rstd1 * D + c1).  chol [55] (decoder LN_q), c1 [256], wg [256,8], out [B,N,6]. */
+int am_cdm_dec_prep(const float* AQ, const float* UU, int NS, const float* g1uu, const float* mu, const float* hu, float* PB,
+                    void* blob, int B, am_stream_t stream);
+int am_cdm_dec_points_tc(const float* x_t, const float* xyz, const float* chol, const float* c1, const float* wg,
+                         const float* PB, const void* blob, float* out, int B, int N, am_stream_t stream);
+
 /* ------------------------------------------------------------------ tcgen05 tensor-core GEMM
  * Same contract as am_linear_f32 for the large layers, computed on the 5th-gen tensor cores with
  * fp32-equivalent accuracy by a 3-term bf16 split (A_lo W_hi + A_hi W_lo + A_hi W_hi), fp32 TMEM

@@ -33,7 +33,8 @@ tot = sum(a["ms"] for a in agg.values())
 print(f"CDM B={B} N={N}: one network evaluation = {tot/3:.3f} ms (sum of kernels)")
 for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
     print(f"  {k:24s} {a['ms']/3:8.3f} ms/step  {a['launches']/3:5.1f} launches  {100*a['ms']/tot:5.1f}%")
-for rep in range(2):
+SHORT = len(sys.argv) > 3 and sys.argv[3] == "short"   # ncu runs: skip the sampling jobs
+for rep in range(0 if SHORT else 2):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     s = diff.ddim_sample_loop(model, (B, N, 6), clip_denoised=False, model_kwargs=kw, eta=0.0)
     torch.cuda.synchronize(); t1 = time.perf_counter()

@@ -19,7 +19,7 @@ set_text_feature_provider(lambda raw: txt)
 kw = dict(c_text=host["texts"], c_pc_xyz=host["xyz"].to(dev), c_pc_contact=host["contact"].to(dev), x_mask=host["x_mask"].to(dev))
 def sync(): torch.cuda.synchronize()
 for rep in range(3):
-    model._cond_cache = (None, None)
+    model._cond_cache = None
     sync(); t0 = time.perf_counter()
     cond = model.encode_condition(Bn.T, **kw); sync(); t1 = time.perf_counter()
     out = diff.p_sample_loop(model, (Bn.B, Bn.T, Bn.DM), clip_denoised=False, model_kwargs=kw); sync(); t2 = time.perf_counter()

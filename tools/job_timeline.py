@@ -19,7 +19,7 @@ txt = host["text"].to(dev)
 set_text_feature_provider(lambda raw: txt)
 kw = dict(c_text=host["texts"], c_pc_xyz=host["xyz"].to(dev), c_pc_contact=host["contact"].to(dev), x_mask=host["x_mask"].to(dev))
 def job():
-    model._cond_cache = (None, None)
+    model._cond_cache = None
     return diff.p_sample_loop(model, (Bn.B, Bn.T, Bn.DM), clip_denoised=False, model_kwargs=kw)
 for _ in range(2):
     job()
