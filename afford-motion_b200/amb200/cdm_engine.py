@@ -162,6 +162,7 @@ class CDMEngine:
         key = (B, N, str(dev))
         ws = self._ws.get(key)
         if ws is None:
+            self._evict()
             DL, C = self.DL, self.C
             e = lambda *s: torch.empty(*s, device=dev)
             nchunk = 1
@@ -175,10 +176,18 @@ class CDMEngine:
             self._ws[key] = ws
         return ws
 
+    def _evict(self, limit=4):
+        """Bound the workspace cache (the general path holds ~1.5 GB per (64, 8192) shape).  Captured graphs bake workspace
+        pointers, so evicting also drops the model's sampler handles."""
+        if len(self._ws) >= limit:
+            self._ws.clear()
+            self.m.__dict__.get("_sampler_handles", {}).clear()
+
     def workspace_collapsed(self, B, N, dev):
         key = ("c", B, N, str(dev))
         ws = self._ws.get(key)
         if ws is None:
+            self._evict()
             DL, C = self.DL, self.C
             d = self.K["dims"]
             AEW, NS = d["KU"] + 2, d["NS"]

@@ -126,10 +126,19 @@ class CMDMEngine:
         return CMDMCondition(B=B, G=G, T=T, static_tokens=static, key_pad=key_pad)
 
     # ------------------------------------------------------------------ workspace
-    def workspace(self, B, S, dev):
-        key = (B, S, str(dev))
+    MAX_WORKSPACES = 4
+
+    def workspace(self, B, G, T, dev):
+        """Activation buffers of one (batch, contact tokens, frames) shape.  Keyed on (B, G, T) — not on S = 2+G+T: captured CUDA
+        graphs bake these pointers, and two jobs with equal S but different (G, T) must not share (and re-allocate) them.
+        Bounded: evicting a workspace also drops the model's sampler handles, whose graphs point into it."""
+        key = (B, G, T, str(dev))
         ws = self._ws.get(key)
         if ws is None:
+            if len(self._ws) >= self.MAX_WORKSPACES:
+                self._ws.clear()
+                self.m.__dict__.get("_sampler_handles", {}).clear()
+            S = 2 + G + T
             D, ff = self.m.latent_dim, self.ff
             M = B * S
             ws = {
@@ -166,7 +175,7 @@ class CMDMEngine:
         G, D = cond.G, m.latent_dim
         S = 2 + G + T
         M = B * S
-        ws = self.workspace(B, S, x.device)
+        ws = self.workspace(B, G, T, x.device)
         self.bind_condition(ws, cond)
         X0 = ws["X0"]
         if self.gemm == "tc":

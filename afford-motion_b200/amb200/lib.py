@@ -38,6 +38,10 @@ _SIGS = _parse_header()
 _lib = None
 
 
+class AmbError(RuntimeError):
+    pass
+
+
 def declared_symbols():
     """Function names declared in include/amb200.h (the boundary a maintainer binds)."""
     txt = open(HEADER_PATH).read()
@@ -59,11 +63,23 @@ def load():
         fn.restype = res
         fn.argtypes = args
     _lib = lib
+    _check_device_once(lib)
     return lib
 
 
-class AmbError(RuntimeError):
-    pass
+def _check_device_once(lib):
+    """Raise on a visible CUDA device that is not sm_100 (the kernels are sm_100a-only SASS).  On a box without a GPU (the CPU
+    build / symbol checks) there is nothing to check: every compute entry point fails at launch there anyway."""
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:  # noqa: BLE001
+        has_gpu = False
+    if has_gpu and lib.am_check_device() != 0:
+        msg = lib.am_last_error()
+        raise AmbError("amb200: the current CUDA device is not compute capability 10.x (B200, sm_100a): "
+                       + (msg.decode() if msg else ""))
+
 
 
 def check(rc: int, what: str):

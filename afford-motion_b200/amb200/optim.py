@@ -79,6 +79,15 @@ class FusedAdamW(torch.optim.Optimizer):
         for group, f in zip(self.param_groups, self._flat):
             if f is None:
                 continue
+            # every p.grad must still be a view of the flat gradient buffer (zero_grad(set_to_none=True) from user code or DDP's
+            # gradient_as_bucket_view detach it): copy stragglers in, treat a missing gradient as zero like the flat kernel does
+            for p, o in zip(f["params"], f["offs"]):
+                gview = f["g"][o:o + p.numel()]
+                if p.grad is None:
+                    gview.zero_()
+                elif p.grad.data_ptr() != f["g"].data_ptr() + 4 * o:
+                    gview.copy_(p.grad.reshape(-1))
+                    p.grad = gview.view(p.shape)
             f["step"] += 1
             b1, b2 = group["betas"]
             _l.check(lib.am_adamw_flat(f["p"].data_ptr(), f["g"].data_ptr(), f["m"].data_ptr(), f["v"].data_ptr(), f["n"],

@@ -134,6 +134,8 @@ class CDM(nn.Module):
                 kwargs = dict(kwargs, c_pc_feat=self.scene_point_features(kwargs["c_pc_xyz"], kwargs.get("c_pc_feat")))
             return cdm_forward_train(self, x.float().contiguous(), timesteps, text, kwargs)
         cond = self.encode_condition(**kwargs)
+        from models.cmdm import _check_timesteps
+        _check_timesteps(timesteps, self.engine.w["time_table"].shape[0])
         t_dev = timesteps.to(device=x.device, dtype=torch.int32).contiguous()
         return self.engine.forward(x.float().contiguous(), t_dev, 1, cond)
 
@@ -160,6 +162,8 @@ class _CDMSamplerHandle:
     def __init__(self, eng, cond, timestep_map):
         from amb200.cdm_engine import CDMCondition
         dev = cond.xyz.device
+        if max(timestep_map) >= eng.w["time_table"].shape[0] or min(timestep_map) < 0:
+            raise IndexError(f"timestep {max(timestep_map)} is out of range for the TimestepEmbedder table ({eng.w['time_table'].shape[0]} rows)")
         idx = torch.as_tensor(list(timestep_map), dtype=torch.long).to(dev)
         self.eng = eng
         self.table = eng.w["time_table"][idx].contiguous()

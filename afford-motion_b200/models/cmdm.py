@@ -120,6 +120,7 @@ class CMDM(nn.Module):
             text = encode_text_clip(self.text_model, kwargs["c_text"], max_length=self.text_max_length, device=x.device).detach().float()
             return cmdm_forward_train(self, x.float().contiguous(), timesteps, text, kwargs)
         cond = self.encode_condition(x.shape[1], **kwargs)
+        _check_timesteps(timesteps, self.engine.w["time_table"].shape[0])
         t_dev = timesteps.to(device=x.device, dtype=torch.int32).contiguous()
         return self.engine.forward(x.float().contiguous(), t_dev, 1, cond)
 
@@ -141,12 +142,22 @@ class CMDM(nn.Module):
         return h
 
 
+def _check_timesteps(timesteps, table_rows):
+    """models/modules.py:50 indexes pe[timesteps]: out-of-range steps raise there; the kernels index device tables unchecked, so
+    the per-call `forward()` path validates on the host (one small D2H read; the device-resident sampling loop validates its
+    timestep map once per handle instead)."""
+    if timesteps.numel() and (int(timesteps.max()) >= table_rows or int(timesteps.min()) < 0):
+        raise IndexError(f"timestep out of range for the TimestepEmbedder table ({table_rows} rows)")
+
+
 class _CMDMSamplerHandle:
     """Persistent per-(shape, timestep map, weight version) sampling state; see CMDM.sampler_begin."""
 
     def __init__(self, eng, cond, timestep_map):
         from amb200.cmdm_engine import CMDMCondition
         dev = cond.static_tokens.device
+        if max(timestep_map) >= eng.w["time_table"].shape[0] or min(timestep_map) < 0:  # the reference's pe[t] raises the same way
+            raise IndexError(f"timestep {max(timestep_map)} is out of range for the TimestepEmbedder table ({eng.w['time_table'].shape[0]} rows)")
         idx = torch.as_tensor(list(timestep_map), dtype=torch.long).to(dev)  # once per handle (a pageable H2D copy synchronises)
         self.eng = eng
         self.table = eng.w["time_table"][idx].contiguous()
@@ -156,7 +167,7 @@ class _CMDMSamplerHandle:
 
     def rebind(self, cond):
         """New job: copy its conditioning into the buffers the captured graph reads."""
-        ws = self.eng.workspace(cond.B, 2 + cond.G + cond.T, cond.static_tokens.device)
+        ws = self.eng.workspace(cond.B, cond.G, cond.T, cond.static_tokens.device)
         ws["cond_id"] = None
         self.eng.bind_condition(ws, cond)
         if self.cond.key_pad is not None:

@@ -4,12 +4,14 @@ CLIP itself is out of scope (third-party frozen tower, no weights offline; SURVE
 results are cached per unique string (the reference re-encodes the same prompts on every denoise step,
 cmdm.py:133-135), and a feature provider can be registered where CLIP is not installed (bench / tests).
 """
+from collections import OrderedDict
 from typing import Callable, List, Optional
 
 import torch
 
 _PROVIDER: Optional[Callable[[List[str]], torch.Tensor]] = None
-_CACHE = {}
+_CACHE = OrderedDict()  # (id(text model), prompt, max_length) -> feature; LRU, bounded
+_CACHE_MAX = 4096
 
 
 def set_text_feature_provider(fn: Optional[Callable[[List[str]], torch.Tensor]]) -> None:
@@ -47,7 +49,8 @@ def encode_text_clip(clip_model: torch.nn.Module, raw_text: List[str], max_lengt
         raise RuntimeError("CLIP is not installed: register a feature provider with "
                            "models.functions.set_text_feature_provider(fn) (fn(list[str]) -> [B,512]).")
     import clip  # type: ignore
-    miss = [s for s in dict.fromkeys(raw_text) if (s, max_length) not in _CACHE]
+    mk = id(clip_model)  # per text tower: two models with different CLIP versions in one process must not share entries
+    miss = [s for s in dict.fromkeys(raw_text) if (mk, s, max_length) not in _CACHE]
     if miss:
         if max_length is not None:
             ctx = max_length + 2
@@ -59,8 +62,13 @@ def encode_text_clip(clip_model: torch.nn.Module, raw_text: List[str], max_lengt
         with torch.no_grad():
             enc = clip_model.encode_text(toks).detach()
         for s, e in zip(miss, enc):
-            _CACHE[(s, max_length)] = e
-    return torch.stack([_CACHE[(s, max_length)] for s in raw_text]).to(device)
+            _CACHE[(mk, s, max_length)] = e
+    out = torch.stack([_CACHE[(mk, s, max_length)] for s in raw_text]).to(device)
+    for s in raw_text:  # LRU order; bounded so a training run over many captions does not pin every feature on the GPU
+        _CACHE.move_to_end((mk, s, max_length))
+    while len(_CACHE) > _CACHE_MAX:
+        _CACHE.popitem(last=False)
+    return out
 
 
 def get_lang_feat_dim_type(model_name: str):
