@@ -42,6 +42,20 @@ class AmbError(RuntimeError):
     pass
 
 
+PRECISIONS = {"parity": 0, "fast": 1}
+
+
+def set_precision(mode: str) -> None:
+    """'parity' (default; 3-term bf16 split = fp32-equivalent, all parity claims) or 'fast' (one bf16 pass, ~1e-2 relative error;
+    outside the parity budget, reported separately by bench.py).  Captured CUDA graphs bake the mode they were captured in:
+    the models' sampler handles are keyed on it."""
+    check(load().am_set_precision(PRECISIONS[mode]), "am_set_precision")
+
+
+def get_precision() -> str:
+    return {v: k for k, v in PRECISIONS.items()}[int(load().am_get_precision())]
+
+
 def declared_symbols():
     """Function names declared in include/amb200.h (the boundary a maintainer binds)."""
     txt = open(HEADER_PATH).read()
@@ -64,6 +78,11 @@ def load():
         fn.argtypes = args
     _lib = lib
     _check_device_once(lib)
+    env = os.environ.get("AMB200_PRECISION")
+    if env:
+        if env not in PRECISIONS:
+            raise AmbError(f"AMB200_PRECISION must be one of {sorted(PRECISIONS)}, got {env!r}")
+        lib.am_set_precision(PRECISIONS[env])
     return lib
 
 

@@ -39,6 +39,7 @@ struct AttParams {
     float* out;               // [B*S, H*64] fp32 or NULL
     __nv_bfloat16* out2;      // [B*S, 2*H*64] bf16 (hi | lo) or NULL
     long long* dbg;           // optional clock64 timeline of CTA 0 (tools/att_timeline.py)
+    int fast;                 // am_set_precision(1): single bf16 pass (Q_hi K_hi^T, P_hi V_hi); the lo tiles are not even loaded
 };
 
 __device__ __forceinline__ uint32_t smem_u32a(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -207,18 +208,18 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tm, AttParams p) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             // K / V of this (batch, head): hi at column h*64 of the K / V thirds, lo 3*D columns further
-            mbar_expect_tx_a(kv_full, 12 * TILE_BYTES);
+            mbar_expect_tx_a(kv_full, (p.fast ? 6 : 12) * TILE_BYTES);
             for (int kt = 0; kt < NKT; ++kt) {
                 tma_load_3d(smem + OFF_KH + kt * TILE_BYTES, &tm, kv_full, D + h * HD, kt * KT, b);
-                tma_load_3d(smem + OFF_KL + kt * TILE_BYTES, &tm, kv_full, 3 * D + D + h * HD, kt * KT, b);
+                if (!p.fast) tma_load_3d(smem + OFF_KL + kt * TILE_BYTES, &tm, kv_full, 3 * D + D + h * HD, kt * KT, b);
                 tma_load_3d(smem + OFF_VH + kt * TILE_BYTES, &tm, kv_full, 2 * D + h * HD, kt * KT, b);
-                tma_load_3d(smem + OFF_VL + kt * TILE_BYTES, &tm, kv_full, 3 * D + 2 * D + h * HD, kt * KT, b);
+                if (!p.fast) tma_load_3d(smem + OFF_VL + kt * TILE_BYTES, &tm, kv_full, 3 * D + 2 * D + h * HD, kt * KT, b);
             }
             for (int t = 0; t < nq; ++t) {
                 if (t > 0) mbar_wait_a(q_empty, (t - 1) & 1);
-                mbar_expect_tx_a(q_full, 2 * TILE_BYTES);
+                mbar_expect_tx_a(q_full, (p.fast ? 1 : 2) * TILE_BYTES);
                 tma_load_3d(smem + OFF_QH, &tm, q_full, h * HD, t * QT, b);
-                tma_load_3d(smem + OFF_QL, &tm, q_full, 3 * D + h * HD, t * QT, b);
+                if (!p.fast) tma_load_3d(smem + OFF_QL, &tm, q_full, 3 * D + h * HD, t * QT, b);
             }
         }
     } else if (warp == 11) {
@@ -242,6 +243,7 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tm, AttParams p) {
 #pragma unroll
                     for (int k = 0; k < HD / 16; ++k) {
                         const uint64_t ko = (uint64_t)(k * 2);  // +32 B per K=16 step inside the 128 B swizzle row
+                        if (p.fast) { umma_ss(d, qh + ko, kh + ko, IDESC_S, k ? 1u : 0u); continue; }
                         umma_ss(d, ql + ko, kh + ko, IDESC_S, k ? 1u : 0u);
                         umma_ss(d, qh + ko, kl + ko, IDESC_S, 1u);
                         umma_ss(d, qh + ko, kh + ko, IDESC_S, 1u);
@@ -262,6 +264,7 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tm, AttParams p) {
                         // the epilogue adds the two 64-column halves.  Measured: three N = 64 MMAs per step ran at ~93 cycles each
                         // (the 4 KB A slice comes from TMEM for every MMA); two MMAs fetch it twice instead of three times.
                         const uint64_t vhl = desc_mnmajor_hilo(sb + OFF_VH + voff + k * 2048), vh = desc_mnmajor(sb + OFF_VH + voff + k * 2048);
+                        if (p.fast) { umma_ts(tmem_base + O_COL, a_hi + k * 8, vh, IDESC_PV, (j | k) ? 1u : 0u); continue; }
                         umma_ts(tmem_base + O_COL, a_hi + k * 8, vhl, IDESC_PV2, (j | k) ? 1u : 0u);
                         umma_ts(tmem_base + O_COL, a_lo + k * 8, vh, IDESC_PV, 1u);
                     }
@@ -353,7 +356,9 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tm, AttParams p) {
             fence_after_a();
             if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[56 + t] = clock64();
             uint32_t o0[32];
-            {
+            if (p.fast) {
+                tmem_ld32a(lane_addr + O_COL + grp * 32, o0);
+            } else {
                 uint32_t o1[32];
                 tmem_ld32a(lane_addr + O_COL + grp * 32, o0);
                 tmem_ld32a(lane_addr + O_COL + HD + grp * 32, o1);   // the P_hi . V_lo term
@@ -438,7 +443,7 @@ extern "C" int am_mha_tc_fwd(const void* qkv2, float* out, void* out2, const uin
         }
         attr = true;
     }
-    AttParams p{B, S, H, scale, key_pad, out, reinterpret_cast<__nv_bfloat16*>(out2), g_att_dbg};
+    AttParams p{B, S, H, scale, key_pad, out, reinterpret_cast<__nv_bfloat16*>(out2), g_att_dbg, am_get_precision()};
     am_launch(mha_tc_kernel, dim3(B * H), dim3(ATT_THREADS), ATT_SMEM, as_stream(stream), 1, tm, p);
     AM_LAUNCH_CHECK("mha_tc_fwd");
     return AM_OK;

@@ -8,6 +8,7 @@
 
 extern "C" void am_set_error_(const char* msg);
 extern "C" void am_count_launch_(int n);
+extern "C" int am_get_precision(void);
 
 #define AM_REQUIRE(cond, code, msg)            \
     do {                                       \

@@ -51,6 +51,7 @@ struct TcParams {
     int vecY;
     long long* dbg;  // optional timeline buffer (tools/tc_timeline.py): CTA (0,0) records clock64() per role
     int res_split;   // MODE 4: `residual` is a bf16 (hi|lo) split tensor [M, 2*ldr] (the previous LayerNorm's only output), not fp32
+    int fast;        // am_set_precision(1): single bf16 pass (A_hi W_hi^T only; the lo halves are neither loaded nor multiplied)
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -805,11 +806,11 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
                     const int s = kbc % NST;
                     mbar_wait(&empty[s], ((kbc / NST) & 1) ^ 1);
                     uint8_t* st = smem + s * STAGE_BYTES;
-                    mbar_expect_tx(&full[s], STAGE_BYTES);
+                    mbar_expect_tx(&full[s], p.fast ? (A_SUB + B_SUB) : STAGE_BYTES);
                     tma_load_2d(st, &tmA, &full[s], kb * BK, m0);                          // A_hi
-                    tma_load_2d(st + A_SUB, &tmA, &full[s], p.Kp + kb * BK, m0);           // A_lo
+                    if (!p.fast) tma_load_2d(st + A_SUB, &tmA, &full[s], p.Kp + kb * BK, m0);           // A_lo
                     tma_load_2d(st + 2 * A_SUB, &tmB, &full[s], kb * BK, n0);              // W_hi
-                    tma_load_2d(st + 2 * A_SUB + B_SUB, &tmB, &full[s], p.Kp + kb * BK, n0);  // W_lo
+                    if (!p.fast) tma_load_2d(st + 2 * A_SUB + B_SUB, &tmB, &full[s], p.Kp + kb * BK, n0);  // W_lo
                 }
             }
         }
@@ -833,6 +834,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         const uint64_t ko = (uint64_t)(k * 2);
+                        if (p.fast) { umma_bf16(d, a_hi + ko, w_hi + ko, IDESC_P, (kb | k) ? 1u : 0u); continue; }
                         umma_bf16(d, a_lo + ko, w_hi + ko, IDESC_P, (kb | k) ? 1u : 0u);
                         umma_bf16(d, a_hi + ko, w_lo + ko, IDESC_P, 1u);
                         umma_bf16(d, a_hi + ko, w_hi + ko, IDESC_P, 1u);
@@ -1116,7 +1118,7 @@ gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 const int m0 = (mp * 2 + (int)cta_rank) * BM;
                 const int nh = n0 + (int)cta_rank * (narrow ? BN_ / 4 : BN_ / 2);
                 const CUtensorMap* tmW = narrow ? &tmBq : &tmB;
-                const uint32_t stage_tx = (uint32_t)(2 * A_SUB + (narrow ? B_SUB : 2 * B_SUB));
+                const uint32_t stage_tx = p.fast ? (uint32_t)(A_SUB + (narrow ? B_SUB / 2 : B_SUB)) : (uint32_t)(2 * A_SUB + (narrow ? B_SUB : 2 * B_SUB));
                 for (int kb = 0; kb < nkb; ++kb, ++kbc) {
                     const int s = kbc % NST;
                     mbar_wait(&empty[s], ((kbc / NST) & 1) ^ 1);   // released in both CTAs by the leader's commit multicast
@@ -1128,9 +1130,9 @@ gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" \
                  ::"r"(dst_), "l"(reinterpret_cast<uint64_t>(map_)), "r"(lbar), "r"(c0_), "r"(c1_) : "memory")
                     AM_TMA_2SM(st, &tmA, kb * BK, m0);                               // A_hi (own 128 rows)
-                    AM_TMA_2SM(st + A_SUB, &tmA, p.Kp + kb * BK, m0);                // A_lo
+                    if (!p.fast) AM_TMA_2SM(st + A_SUB, &tmA, p.Kp + kb * BK, m0);   // A_lo
                     AM_TMA_2SM(st + 2 * A_SUB, tmW, kb * BK, nh);                    // W_hi, own half of the n-tile
-                    AM_TMA_2SM(st + 2 * A_SUB + B_SUB, tmW, p.Kp + kb * BK, nh);     // W_lo
+                    if (!p.fast) AM_TMA_2SM(st + 2 * A_SUB + B_SUB, tmW, p.Kp + kb * BK, nh);     // W_lo
 #undef AM_TMA_2SM
                 }
             }
@@ -1159,6 +1161,7 @@ gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #define AM_UMMA_2SM(a_, b_, acc_)                                                                                     \
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" \
                  ::"r"(d), "l"(a_), "l"(b_), "r"(idesc), "r"((uint32_t)(acc_)) : "memory")
+                        if (p.fast) { AM_UMMA_2SM(a_hi + ko, w_hi + ko, (kb | k) ? 1u : 0u); continue; }
                         AM_UMMA_2SM(a_lo + ko, w_hi + ko, (kb | k) ? 1u : 0u);
                         AM_UMMA_2SM(a_hi + ko, w_lo + ko, 1u);
                         AM_UMMA_2SM(a_hi + ko, w_hi + ko, 1u);
@@ -1335,7 +1338,8 @@ extern "C" int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp
         CUtensorMap tmA, tmB;
         AM_REQUIRE(make_map(&tmA, A2, (uint64_t)M, (uint64_t)2 * Kp, 32, BM), AM_ELAUNCH, "am_linear_tc: cuTensorMapEncodeTiled(A) failed");
         AM_REQUIRE(make_map(&tmB, W2, (uint64_t)N, (uint64_t)2 * Kp, 32, bn), AM_ELAUNCH, "am_linear_tc: cuTensorMapEncodeTiled(W) failed");
-        TcParams p{M, N, Kp, bias, act, residual, ldr, res_mod, Y, ldy, yin_g, yout_g, y_off, reinterpret_cast<__nv_bfloat16*>(Y2), Np2, 0, g_tc_dbg, res_split};
+        TcParams p{M, N, Kp, bias, act, residual, ldr, res_mod, Y, ldy, yin_g, yout_g, y_off, reinterpret_cast<__nv_bfloat16*>(Y2), Np2, 0, g_tc_dbg, res_split, 0};
+        p.fast = am_get_precision();
         p.vecY = Y && (reinterpret_cast<uintptr_t>(Y) & 15u) == 0 && (ldy % 4 == 0);
         const int grid = total < AM_NUM_SMS ? total : AM_NUM_SMS;
         cudaStream_t st = as_stream(stream);

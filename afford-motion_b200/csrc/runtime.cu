@@ -18,3 +18,13 @@ extern "C" int am_check_device(void) {
     if (major != 10) { am_set_error_("amb200 kernels are compiled for sm_100a only"); return AM_EARCH; }
     return AM_OK;
 }
+
+// Precision mode of the tensor-core kernels (am_linear_tc, am_mha_tc_fwd): 0 = parity (3-term bf16 split, fp32-equivalent, the
+// default and the mode every parity number is quoted in), 1 = fast (single bf16 pass: hi x hi only, ~1e-2 relative error).
+static std::atomic<int> g_precision{0};
+extern "C" int am_set_precision(int mode) {
+    if (mode != 0 && mode != 1) { am_set_error_("am_set_precision: mode must be 0 (parity) or 1 (fast)"); return AM_EINVAL; }
+    g_precision.store(mode);
+    return AM_OK;
+}
+extern "C" int am_get_precision(void) { return g_precision.load(); }

@@ -299,7 +299,9 @@ class GaussianDiffusion:
                 trace.append((label, _time.perf_counter()))
         _tr("loop_begin")
         with th.no_grad():
-            handle = model.sampler_begin(tuple(img.shape), model_kwargs, tmap)
+            from amb200.trace import rng as _nvtx
+            with _nvtx("encode_condition"):
+                handle = model.sampler_begin(tuple(img.shape), model_kwargs, tmap)
             _tr("sampler_begin_done")
             n = self.num_timesteps
             plans = getattr(handle, "plans", None)
@@ -320,7 +322,8 @@ class GaussianDiffusion:
             seed_dev.fill_(int(seed))
 
             def one_step(nz=None):
-                handle.forward(img, t_dev, x0)
+                with _nvtx("network_eval"):
+                    handle.forward(img, t_dev, x0)
                 if kind == "ddpm":
                     ops.p_sample_update(x0, img, img, nz, tab["coef1"], tab["coef2"], tab["logvar"], t_dev, 0, seed_dev=seed_dev,
                                         sample0=self.sample_offset)
@@ -357,7 +360,7 @@ class GaussianDiffusion:
                     _t0 = _time.perf_counter()
                     graph = th.cuda.CUDAGraph()
                     c0 = _lib.launch_count()
-                    with th.cuda.graph(graph):
+                    with _nvtx("graph_capture"), th.cuda.graph(graph):
                         for _ in range(plan["unroll"]):
                             one_step()
                     plan["per_graph"] = captured_now = _lib.launch_count() - c0
@@ -365,7 +368,8 @@ class GaussianDiffusion:
                     self.last_capture_ms = 1e3 * (_time.perf_counter() - _t0)  # host cost of capture + instantiate
                     _tr("capture_done")
                 elif n - k >= plan["unroll"]:
-                    plan["graph"].replay()
+                    with _nvtx("denoise_steps"):
+                        plan["graph"].replay()
                     replays += 1
                     done = plan["unroll"]
                 else:

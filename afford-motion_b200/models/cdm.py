@@ -145,7 +145,8 @@ class CDM(nn.Module):
         cond = self.encode_condition(use_cache=False, **model_kwargs)  # once per job, never from a cache
         eng = self.engine
         pf = cond.point_feat
-        key = (tuple(shape), tuple(timestep_map), eng._version, None if pf is None else tuple(pf.shape), str(cond.xyz.device))
+        from amb200 import lib as _lib
+        key = (tuple(shape), tuple(timestep_map), eng._version, _lib.get_precision(), None if pf is None else tuple(pf.shape), str(cond.xyz.device))
         handles = self.__dict__.setdefault("_sampler_handles", {})
         h = handles.get(key)
         if h is None:

@@ -131,7 +131,8 @@ class CMDM(nn.Module):
         the same shape replay the first job's graph."""
         cond = self.encode_condition(shape[1], use_cache=False, **model_kwargs)  # once per job, never from a cache
         eng = self.engine
-        key = (tuple(shape), tuple(timestep_map), eng._version, cond.key_pad is None, cond.G, str(cond.static_tokens.device))
+        from amb200 import lib as _lib
+        key = (tuple(shape), tuple(timestep_map), eng._version, _lib.get_precision(), cond.key_pad is None, cond.G, str(cond.static_tokens.device))
         handles = self.__dict__.setdefault("_sampler_handles", {})
         h = handles.get(key)
         if h is None:

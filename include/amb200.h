@@ -40,6 +40,12 @@ typedef void* am_stream_t; /* cudaStream_t */
 #define AM_ACT_AFTER_RES 16 /* OR-ed flag: y = act(xW^T + bias + residual) instead of act(..) + residual */
 
 int am_version(void);
+/* Precision mode of the tensor-core kernels (am_linear_tc, am_mha_tc_fwd), process-global:
+ *   0 = parity (default): every product as a 3-term bf16 split with fp32 accumulation — fp32-equivalent, the mode all parity
+ *       claims (1e-3 max-abs vs the reference, BASELINE.json north_star) are made in;
+ *   1 = fast: ONE bf16 pass (hi x hi), about 1e-2 relative error per layer — outside the parity budget, reported separately. */
+int am_set_precision(int mode);
+int am_get_precision(void);
 /* 0 if the current device is compute capability 10.x, AM_EARCH otherwise */
 int am_check_device(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
