@@ -43,7 +43,10 @@ class CDMEngine:
         self.gemm = os.environ.get("AMB200_GEMM", "tc")  # tcgen05 (default) or fp32 SIMT for the per-point MLP GEMM
         # point path: "collapsed" (default when cin == 9: rank-collapsed kernels of csrc/perceiver_tc.cu) or "general"
         self.point_path = os.environ.get("AMB200_CDM_POINTS", "collapsed")
+        # latent side of the collapsed path: "fused" (two cluster kernels, csrc/perceiver_latent.cu) or "layers" (one launch per layer)
+        self.latent_path = os.environ.get("AMB200_CDM_LATENT", "fused")
         self.K = None
+        self.latw = None
 
     def refresh(self):
         v = params_version(self.m)
@@ -145,7 +148,31 @@ class CDMEngine:
         if cm.encoder_adapter.in_features == 9 and self.out_dim == 6 and self.He == 8 and self.Hd == 8:
             self.K = {k: (t.to(dev) if torch.is_tensor(t) else t) for k, t in fold_constants(m).items()}
         self.w = w
+        self.latw = None
+        if self.K is not None and DL == 512 and C == 256 and self.n_self == 2 and hd == 64 and hdd == 32 and mlp[1].out_features == DL:
+            self.latw = self._latent_table(w, self.K)
         self._version = v
+
+    def _latent_table(self, w, K):
+        """HOST pointer table of the fused latent-chain kernels (order of `struct LatW`, csrc/perceiver_latent.cu); weights are
+        re-laid out K-major ([K][N]) once per weight version.  Returns (ctypes array, count, keep-alive tensors)."""
+        import ctypes
+        from . import lib as _l
+        T = lambda t: t.t().contiguous()  # noqa: E731
+        order = [w["la_w"],  # unused slot (keeps the table aligned with the struct)
+                 w["e_qn_g"], w["e_qn_b"], T(w["e_q_w"]), w["e_q_b"], K["e_kfold"], K["e_ecg"], K["e_beta"],
+                 T(w["e_v_w"]), w["e_v_b"], T(w["e_o_w"]), w["e_o_b"],
+                 w["e_m_g"], w["e_m_b"], T(w["e_m1_w"]), w["e_m1_b"], T(w["e_m2_w"]), w["e_m2_b"]]
+        for name in ("n_g", "n_b", "qkv_w", "qkv_b", "o_w", "o_b", "m_g", "m_b", "m1_w", "m1_b", "m2_w", "m2_b"):
+            for i in range(2):
+                t = w[f"s{i}_{name}"]
+                order.append(T(t) if name.endswith("_w") else t)
+        order += [w["d_kvn_g"], w["d_kvn_b"], T(w["d_kv_w"]), w["d_kv_b"], K["d_qfold"], T(K["d_ostack"])]
+        n = int(_l.load().am_cdm_latent_nweights())
+        assert len(order) == n, (len(order), n)
+        assert all(t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda for t in order)
+        arr = (ctypes.c_void_p * n)(*[t.data_ptr() for t in order])
+        return arr, n, order
 
     # ------------------------------------------------------------------ conditioning (once per batch)
     @torch.no_grad()
@@ -222,6 +249,18 @@ class CDMEngine:
             cx = x.shape[-1]
         collapsed = self.is_collapsed(cond)
         ws = self.workspace_for(cond)
+        if collapsed and self.latw is not None and self.latent_path == "fused":
+            K = self.K
+            NS = K["dims"]["NS"]
+            tt = w["time_table"] if time_table is None else time_table
+            if out is None:
+                out = torch.empty(B, N, self.out_dim, device=dev)
+            ops.cdm_latent_pre(self.latw, cond.text_latent, tt, t_dev, t_stride, ws["AE"], B)
+            ops.cdm_enc_points(x, cond.xyz, K["e_chol"], ws["AE"], ws["PART"], B, N, ws["nchunk"])
+            ops.cdm_latent_post(self.latw, cond.text_latent, tt, t_dev, t_stride, ws["PART"], ws["nchunk"], ws["AQ"], ws["UU"], NS, B)
+            ops.cdm_dec_prep(ws["AQ"], ws["UU"], NS, K["d_g1uu"], K["d_mu"], K["d_hu"], ws["PB"], ws["BLOB"], B)
+            ops.cdm_dec_points_tc(x, cond.xyz, K["d_chol"], K["d_c1"], K["d_wg"], ws["PB"], ws["BLOB"], out, B, N)
+            return out
         if ws["cond_id"] is not cond:
             ws["L0"][:, 0, :].copy_(cond.text_latent)
             ws["cond_id"] = cond

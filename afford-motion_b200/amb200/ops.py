@@ -215,6 +215,19 @@ def cdm_dec_points_tc(x_t, xyz, chol, c1, wg, PB, blob, out, B, N):
     return out
 
 
+def cdm_latent_pre(wtab, text_latent, time_table, t, t_stride, AE, B):
+    """wtab: (ctypes pointer array, count) built by CDMEngine (see am_cdm_latent_pre)."""
+    _chk_cuda(text_latent, time_table, t, AE)
+    _l.check(_l.load().am_cdm_latent_pre(wtab[0], wtab[1], _ptr(_f32c(text_latent)), _ptr(_f32c(time_table)), _ptr(t), t_stride, _ptr(AE), B,
+                                        _stream()), "am_cdm_latent_pre")
+
+
+def cdm_latent_post(wtab, text_latent, time_table, t, t_stride, part, nchunk, AQ, UU, NS, B):
+    _chk_cuda(text_latent, time_table, t, part, AQ, UU)
+    _l.check(_l.load().am_cdm_latent_post(wtab[0], wtab[1], _ptr(_f32c(text_latent)), _ptr(_f32c(time_table)), _ptr(t), t_stride, _ptr(part),
+                                         nchunk, _ptr(AQ), _ptr(UU), NS, B, _stream()), "am_cdm_latent_post")
+
+
 def linear_skinny(x1, K1, x2, K2, W, bias, y, M, N, ldx1=None, ldx2=None, ldy=None):
     _l.check(_l.load().am_linear_skinny(_ptr(x1), K1 if ldx1 is None else ldx1, K1, _ptr(x2), (K2 if ldx2 is None else ldx2), K2, _ptr(W),
                                        _ptr(bias), _ptr(y), N if ldy is None else ldy, M, N, _stream()), "am_linear_skinny")
@@ -307,5 +320,5 @@ def _wrap(name, fn):
 for _n in ("randn_", "p_sample_update", "ddim_update", "q_sample", "masked_mse", "add_i32", "linear", "linear_batched", "layernorm", "mha_fwd",
            "gather_time_token", "gather_rows", "furthestsampling", "knnquery", "pt_layer_fwd", "transition_down_fwd", "interpolation", "segment_mean",
            "cdm_encoder_partial", "cdm_encoder_combine", "cdm_decoder_point", "cdm_enc_points", "cdm_enc_expand", "cdm_dec_prep",
-           "cdm_dec_points_tc", "linear_skinny", "split_bf16", "linear_tc", "mha_tc_fwd"):
+           "cdm_dec_points_tc", "cdm_latent_pre", "cdm_latent_post", "linear_skinny", "split_bf16", "linear_tc", "mha_tc_fwd"):
     globals()[_n] = _wrap(_n, globals()[_n])

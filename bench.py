@@ -443,6 +443,35 @@ def main():
                             "(DESIGN.md 4.1), so issued tensor work is 3x and frac cannot exceed 1/3"}
 
     extra = {}
+    done = threading.Event()
+
+    def _emit(extra_now, note=None):
+        line = {"metric": METRIC, "value": value, "unit": "denoise-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "fp32 (tensor-core GEMMs as 3-term bf16 split with fp32 accumulation; elementwise / softmax / LayerNorm fp32)", "data": "synthetic",
+                "config": bench_config(world, nd),
+                "notes": {"bench_step": "one full sampling job incl. conditioning encode (FPS / kNN / PointTransformer contact encoder)",
+                          "l2": "256 MB buffer written between jobs (L2 flush); per-step working set > 126 MB L2",
+                          "loop": "one CUDA graph of 8 denoise steps, captured by the first job and replayed by every later one",
+                          "motions_per_s": value * B / nd, "tflops_algorithmic": value * B / world * GFLOP_PER_SAMPLE_STEP / 1e3,
+                          "conditioning_launches_per_job": cond_launches, "extra_legs": note or "completed"},
+                "e2e": {"value": e2e_value, "unit": "denoise-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches_per_job * args.steps), "clocks": extra_now.pop("_clocks", None), "roofline": roof,
+                "cpu_baseline": extra_now.pop("_cpu_baseline", None),
+                "kernels": prof_out, "job_ms": job_ms, "graph_capture_ms_per_job": getattr(diff, "last_capture_ms", None)}
+        line.update(extra_now)
+        print(json.dumps(line), flush=True)
+
+    def _watchdog():
+        # An extra leg (the only ones with data-path collectives are config 4's) must never take the headline down with it: if the
+        # legs have not finished within the budget, every rank gives up and rank 0 emits the line with what it has.
+        if done.wait(float(os.environ.get("AMB200_BENCH_EXTRA_BUDGET_S", "420"))):
+            return
+        if rank == 0:
+            _emit(dict(extra), note="aborted by the watchdog (an extra leg exceeded its time budget); headline numbers are complete")
+        os._exit(0)
+    threading.Thread(target=_watchdog, daemon=True).start()
     if not args.no_extra:
         # ------------------------------------------------------------------ fast mode (single bf16 pass), same jobs
         try:
@@ -523,13 +552,15 @@ def main():
                 text_dev["t"] = t5
                 m, c = two_stage_generate(cdm5, cdiff5, model, diff, texts5, xyz5, xm5, (T, DM), contact_mean=0.2, contact_std=0.3, ddim=True)
                 return m
-            c5()
-            k5 = 2
+            for _ in range(2):
+                c5()
+            k5 = 4
             ms5 = timed(c5, k5, "config5")
             extra["config5"] = {
                 "workload": "two-stage CDM (100 DDIM of 500) -> on-device contact hand-off -> CMDM (1000 DDPM), batch=16 in total "
                             f"({B5} per GPU), N=8192 (configs[4])",
                 "value": k5 * B5 * world / (ms5 / 1e3), "unit": "motions/s", "ms_per_job": ms5 / k5, "n_gpus": world, "scaling": "strong",
+                "median_ms_per_job_rank0": sorted(job_ms["config5"])[k5 // 2],
                 "denoise_steps_per_s": k5 * 1100 * world / (ms5 / 1e3)}
             del cdm5, cdiff5
         except Exception as e:  # noqa: BLE001
@@ -579,28 +610,14 @@ def main():
         except Exception as e:  # noqa: BLE001
             extra["config4"] = {"error": repr(e)[:300]}
 
-    clk = clocks.stop() if rank == 0 else None
-
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_baseline_subprocess("headline", 6, 1)
-
+    clk = clocks.stop() if rank == 0 else None
+    done.set()
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": "denoise-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "fp32 (tensor-core GEMMs as 3-term bf16 split with fp32 accumulation; elementwise / softmax / LayerNorm fp32)", "data": "synthetic",
-                "config": bench_config(world, nd),
-                "notes": {"bench_step": "one full sampling job incl. conditioning encode (FPS / kNN / PointTransformer contact encoder)",
-                          "l2": "256 MB buffer written between jobs (L2 flush); per-step working set > 126 MB L2",
-                          "loop": "one CUDA graph of 8 denoise steps, captured by the first job and replayed by every later one",
-                          "motions_per_s": value * B / nd, "tflops_algorithmic": value * B / world * GFLOP_PER_SAMPLE_STEP / 1e3,
-                          "conditioning_launches_per_job": cond_launches},
-                "e2e": {"value": e2e_value, "unit": "denoise-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": int(launches_per_job * args.steps), "clocks": clk, "roofline": roof, "cpu_baseline": cpu_base,
-                "kernels": prof_out, "job_ms": job_ms, "graph_capture_ms_per_job": getattr(diff, "last_capture_ms", None)}
-        line.update(extra)
-        print(json.dumps(line))
+        extra["_clocks"], extra["_cpu_baseline"] = clk, cpu_base
+        _emit(extra)
     if world > 1:
         dist.destroy_process_group()
 

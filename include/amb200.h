@@ -228,6 +228,23 @@ int am_cdm_dec_prep(const float* AQ, const float* UU, int NS, const float* g1uu,
 int am_cdm_dec_points_tc(const float* x_t, const float* xyz, const float* chol, const float* c1, const float* wg,
                          const float* PB, const void* blob, float* out, int B, int N, am_stream_t stream);
 
+/* ------------------------------------------------------------------ CDM Perceiver, latent side as two cluster kernels
+ * The 2 latent tokens per sample (language + time; models/cdm.py:176-185, Perceiver-IO blocks models/modules.py:504-648): 25
+ * dependent layers on [2B, 512] activations.  One thread-block cluster of 8 CTAs owns 4 samples; every CTA holds the activation
+ * block in shared memory, computes 1/8 of each layer's columns from K-major weights and broadcasts its slice through distributed
+ * shared memory; layers are separated by a cluster barrier instead of a kernel launch (29 launches -> 2 per denoise step).
+ *   W = HOST array of am_cdm_latent_nweights() device pointers, order of `struct LatW` in csrc/perceiver_latent.cu (weights
+ *   K-major [K][N] fp32).  text_latent [B,512] = language_adapter(text); time_table [steps,512] =
+ *   time_embedding_adapter(TimestepEmbedder(t)); t DEVICE int32 (t_stride 0: shared, 1: per sample).
+ *   am_cdm_latent_pre  -> AE [B,16,12]   (input of am_cdm_enc_points)
+ *   am_cdm_latent_post : part [B,nchunk,16,12] (output of am_cdm_enc_points) -> AQ [B,16,12], UU [B,16,NS]
+ *                        (inputs of am_cdm_dec_prep). */
+int am_cdm_latent_nweights(void);
+int am_cdm_latent_pre(const void* const* W, int nW, const float* text_latent, const float* time_table, const int32_t* t,
+                      int t_stride, float* AE, int B, am_stream_t stream);
+int am_cdm_latent_post(const void* const* W, int nW, const float* text_latent, const float* time_table, const int32_t* t,
+                       int t_stride, const float* part, int nchunk, float* AQ, float* UU, int NS, int B, am_stream_t stream);
+
 /* ------------------------------------------------------------------ tcgen05 tensor-core GEMM
  * Same contract as am_linear_f32 for the large layers, computed on the 5th-gen tensor cores with
  * fp32-equivalent accuracy by a 3-term bf16 split (A_lo W_hi + A_hi W_lo + A_hi W_hi), fp32 TMEM

@@ -59,8 +59,8 @@ def install_third_party_stubs(cpu_pointops: bool = True):
     def _hydra_main(*a, **k):
         return lambda fn: fn
     _mod("hydra", main=_hydra_main)
-    if "clip" not in sys.modules:
-        _mod("clip")
+    if cpu_pointops and "clip" not in sys.modules:
+        _mod("clip")  # only for the reference's models/functions.py; the drop-in detects a missing `clip` by ImportError
     _mod("smplkit", SMPLXLayer=lambda **k: None)
     _mod("natsort", natsorted=sorted)
     try:

@@ -19,7 +19,7 @@ def _mk(N, steps=500, respacing=""):
     return model.to(DEV).eval(), diff
 
 
-@pytest.mark.parametrize("B,N", [(2, 1024), (3, 1000), (1, 77), (8, 8192)])
+@pytest.mark.parametrize("B,N", [(2, 1024), (3, 1000), (1, 77), (8, 8192), (5, 512)])
 def test_collapsed_forward_vs_oracle_and_general_path(B, N):
     """Config-1 shape, ragged tile counts (N not a multiple of 128 / smaller than one tile) and the config-3 per-GPU shard
     (B=8, N=8192): collapsed kernels vs the straight oracle; and vs the general (unfolded-per-point) CUDA kernels."""
@@ -40,12 +40,17 @@ def test_collapsed_forward_vs_oracle_and_general_path(B, N):
             ref = cdm_ref.cdm_forward({k: v.detach().cpu() for k, v in model.state_dict().items()}, x, t, txt, xyz)
             err = (out.cpu() - ref).abs().max().item()
             assert err < 1e-4, err  # budget NET_TOL; the collapsed path's measured noise floor is ~3e-6
+            assert model.engine.latw is not None and model.engine.latent_path == "fused"  # the cluster kernels ran
+            model.engine.latent_path = "layers"   # same collapsed point kernels, latent side as one launch per layer
+            out_l = model(x.to(DEV), t.to(DEV), **kw)
+            assert (out_l - out).abs().max().item() < 2e-5
             model.engine.point_path = "general"
             model._cond_cache = None
             out_g = model(x.to(DEV), t.to(DEV), **kw)
             assert (out_g - out).abs().max().item() < 1e-4
     finally:
         model.engine.point_path = "collapsed"
+        model.engine.latent_path = "fused"
         set_text_feature_provider(None)
 
 
