@@ -81,14 +81,21 @@ __device__ __forceinline__ void lat_gemm(const float* __restrict__ Xs, int ldx, 
 #pragma unroll
         for (int r = 0; r < R; ++r) xrow[r] = HEADROWS ? Xs + ((r >> 1) * R16 + 2 * (n / HD) + (r & 1)) * ldx : Xs + r * ldx;
         const float* w = WT + (int64_t)(kq * kper) * N + n;
-#pragma unroll 2
-        for (int k = 0; k < kper; k += 4) {
-            const float w0 = __ldg(w), w1 = __ldg(w + N), w2 = __ldg(w + 2 * N), w3 = __ldg(w + 3 * N);
-            w += 4 * (int64_t)N;
+        // the layer is latency-bound on the weight stream (each lane walks one column, 128-byte warp requests): keep 32 loads in
+        // flight per lane (KB rows of W at a time) before the FMAs consume them
+        constexpr int KB = 32;
+        for (int k = 0; k < kper; k += KB) {
+            float wv[KB];
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const float4 x = *reinterpret_cast<const float4*>(xrow[r] + kq * kper + k);
-                acc[r] = fmaf(x.x, w0, fmaf(x.y, w1, fmaf(x.z, w2, fmaf(x.w, w3, acc[r]))));
+            for (int j = 0; j < KB; ++j) wv[j] = __ldg(w + (int64_t)j * N);
+            w += (int64_t)KB * N;
+#pragma unroll
+            for (int j = 0; j < KB; j += 4) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const float4 x = *reinterpret_cast<const float4*>(xrow[r] + kq * kper + k + j);
+                    acc[r] = fmaf(x.x, wv[j], fmaf(x.y, wv[j + 1], fmaf(x.z, wv[j + 2], fmaf(x.w, wv[j + 3], acc[r]))));
+                }
             }
         }
         __syncthreads();  // `red` of the previous pass / layer fully consumed

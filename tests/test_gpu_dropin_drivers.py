@@ -85,7 +85,7 @@ def test_reference_test_py_drives_the_dropin(drivers, tmp_path):
     txt = synth.text_features(8, seed=61)
     set_text_feature_provider(lambda raw: txt[: len(raw)])
     try:
-        rtest.test(cfg)  # test.py:14-130, unmodified
+        rtest.main(cfg)  # test.py:14-130 through its own main() (test.py:105-129; hydra.main is a no-op decorator here), unmodified
     finally:
         set_text_feature_provider(None)
     samples, ksamples = ev.got

@@ -7,7 +7,7 @@ OUT=gpurun_out/sanitize
 mkdir -p $OUT
 SMOKE="python -c 'import __graft_entry__ as g; g.smoke()'"
 run() {  # tool, tag, command
-  timeout 900 compute-sanitizer --tool "$1" --print-limit 20 --error-exitcode 7 bash -c "$3" > "$OUT/$2.log" 2>&1
+  timeout 420 compute-sanitizer --tool "$1" --print-limit 20 --error-exitcode 7 bash -c "$3" > "$OUT/$2.log" 2>&1
   echo "$2: exit=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' "$OUT/$2.log" | tail -1)" | tee -a "$OUT/summary.txt"
 }
 : > "$OUT/summary.txt"
