@@ -11,7 +11,8 @@ from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_uint64, c_void_
 _HERE = os.path.dirname(os.path.abspath(__file__))
 PKG_ROOT = os.path.dirname(_HERE)
 REPO_ROOT = os.path.dirname(PKG_ROOT)
-LIB_PATH = os.path.join(PKG_ROOT, "csrc", "libamb200.so")
+# AMB200_LIB: A/B timing of another BUILD of this library (tools/ab_tc.py); never a different implementation
+LIB_PATH = os.environ.get("AMB200_LIB") or os.path.join(PKG_ROOT, "csrc", "libamb200.so")
 HEADER_PATH = os.path.join(REPO_ROOT, "include", "amb200.h")
 
 _CT = {"double": ctypes.c_double, "int": c_int, "int32_t": c_int32, "int64_t": c_int64, "uint64_t": c_uint64, "uint32_t": ctypes.c_uint32, "float": c_float,
@@ -73,13 +74,15 @@ def load():
             "(or `make -C afford-motion_b200/csrc`). There is no CPU/PyTorch fallback for the hot path.")
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in _SIGS.items():
+        if os.environ.get("AMB200_LIB") and not hasattr(lib, name):
+            continue  # an older build under A/B test lacks the newer entry points
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
     _lib = lib
     _check_device_once(lib)
     env = os.environ.get("AMB200_PRECISION")
-    if env:
+    if env and hasattr(lib, "am_set_precision"):
         if env not in PRECISIONS:
             raise AmbError(f"AMB200_PRECISION must be one of {sorted(PRECISIONS)}, got {env!r}")
         lib.am_set_precision(PRECISIONS[env])

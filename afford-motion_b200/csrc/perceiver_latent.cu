@@ -5,7 +5,7 @@
 // 18 MB of weights — was the whole CDM step at the config-3 shard (8 samples per GPU: ~200 us of ~250 us, launch-latency bound).
 // Here one cluster of 8 CTAs owns 4 samples (8 activation rows).  Every CTA keeps a full copy of the 8 x 512 activation block in
 // shared memory, computes 1/8 of each layer's output columns (weights stored K-major [K][N]: lane = column, coalesced 128-byte
-// reads; K split over 4 warps, partial sums combined through shared memory) and broadcasts its slice into all 8 CTAs' buffers
+// reads; K split over 8 warps, partial sums combined through shared memory) and broadcasts its slice into all 8 CTAs' buffers
 // through distributed shared memory; layers are separated by one cluster barrier (~0.4 us) instead of a kernel launch.
 //   cdm_latent_pre_kernel  : L0 = [language latent ; time table[t]] -> LN_q -> q_proj (scaled) -> AE = per-head fold of the query
 //                            against the collapsed key matrices  (input of cdm_enc_points_kernel)
@@ -29,10 +29,11 @@ constexpr int KU = 10, AEW = KU + 2;
 constexpr int NC = 8;          // CTAs per cluster (one per head in the per-head stages)
 constexpr int SPC = 4;         // samples per cluster
 constexpr int R = 2 * SPC;     // activation rows per cluster
-constexpr int LT = 256;        // threads per CTA
+constexpr int LT = 512;        // threads per CTA: 16 warps = 2 column groups x 8 K splits
+constexpr int KS = 8;          // K splits per layer
 constexpr int LQKV = 3 * DL;
-// shared memory (floats): X0 stream | X1 | XQ [R][1536] | X2 [R][512] | red [4][R][64]   (Z [SPC][16][256] aliases XQ..X2)
-constexpr int SX0 = 0, SX1 = SX0 + R * DL, SXQ = SX1 + R * DL, SX2 = SXQ + R * LQKV, SRED = SX2 + R * DL, SEND = SRED + 4 * R * 64;
+// shared memory (floats): X0 stream | X1 | XQ [R][1536] | X2 [R][512] | red [KS][R][64]   (Z [SPC][16][256] aliases XQ..X2)
+constexpr int SX0 = 0, SX1 = SX0 + R * DL, SXQ = SX1 + R * DL, SX2 = SXQ + R * LQKV, SRED = SX2 + R * DL, SEND = SRED + KS * R * 64;
 static_assert(SPC * R16 * C <= R * LQKV + R * DL, "Z must fit in the XQ|X2 alias");
 constexpr int LAT_SMEM = SEND * 4;
 
@@ -71,7 +72,7 @@ __device__ __forceinline__ void lat_gemm(const float* __restrict__ Xs, int ldx, 
     const int warp = tid >> 5, lane = tid & 31;
     const int cg = warp & 1, kq = warp >> 1;
     const int ncol = N / NC;          // 64 (N = 512) or 192 (N = 1536)
-    const int kper = K >> 2;
+    const int kper = K / KS;
     for (int c0 = 0; c0 < ncol; c0 += 64) {
         const int n = (int)rank * ncol + c0 + cg * 32 + lane;
         float acc[R];
@@ -105,7 +106,9 @@ __device__ __forceinline__ void lat_gemm(const float* __restrict__ Xs, int ldx, 
         for (int i = tid; i < R * 64; i += LT) {
             const int r = i >> 6, c = i & 63;
             const int nn = (int)rank * ncol + c0 + c;
-            float v = red[(0 * R + r) * 64 + c] + red[(1 * R + r) * 64 + c] + red[(2 * R + r) * 64 + c] + red[(3 * R + r) * 64 + c];
+            float v = 0.f;
+#pragma unroll
+            for (int q = 0; q < KS; ++q) v += red[(q * R + r) * 64 + c];
             if (bias) v += __ldg(bias + nn);
             if (ACT == AM_ACT_GELU) v = gelu_erf(v);
             if (RES) v += RES[r * ldy + nn];
