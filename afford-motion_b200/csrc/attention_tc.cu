@@ -16,6 +16,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <math_constants.h>
+#include <type_traits>
 #include "common.cuh"
 
 namespace {
@@ -207,24 +208,31 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tm, AttParams p) {
     if (warp == 10) {
         // ===================== TMA producer =====================
         if (lane == 0) {
+            // FAST is resolved once per role (a per-MMA `if (p.fast)` in these single-thread loops cost 12 % of the kernel)
+            auto produce = [&](auto fc) {
+            constexpr bool FAST = decltype(fc)::value;
             // K / V of this (batch, head): hi at column h*64 of the K / V thirds, lo 3*D columns further
-            mbar_expect_tx_a(kv_full, (p.fast ? 6 : 12) * TILE_BYTES);
+            mbar_expect_tx_a(kv_full, (FAST ? 6 : 12) * TILE_BYTES);
             for (int kt = 0; kt < NKT; ++kt) {
                 tma_load_3d(smem + OFF_KH + kt * TILE_BYTES, &tm, kv_full, D + h * HD, kt * KT, b);
-                if (!p.fast) tma_load_3d(smem + OFF_KL + kt * TILE_BYTES, &tm, kv_full, 3 * D + D + h * HD, kt * KT, b);
+                if (!FAST) tma_load_3d(smem + OFF_KL + kt * TILE_BYTES, &tm, kv_full, 3 * D + D + h * HD, kt * KT, b);
                 tma_load_3d(smem + OFF_VH + kt * TILE_BYTES, &tm, kv_full, 2 * D + h * HD, kt * KT, b);
-                if (!p.fast) tma_load_3d(smem + OFF_VL + kt * TILE_BYTES, &tm, kv_full, 3 * D + 2 * D + h * HD, kt * KT, b);
+                if (!FAST) tma_load_3d(smem + OFF_VL + kt * TILE_BYTES, &tm, kv_full, 3 * D + 2 * D + h * HD, kt * KT, b);
             }
             for (int t = 0; t < nq; ++t) {
                 if (t > 0) mbar_wait_a(q_empty, (t - 1) & 1);
-                mbar_expect_tx_a(q_full, (p.fast ? 1 : 2) * TILE_BYTES);
+                mbar_expect_tx_a(q_full, (FAST ? 1 : 2) * TILE_BYTES);
                 tma_load_3d(smem + OFF_QH, &tm, q_full, h * HD, t * QT, b);
-                if (!p.fast) tma_load_3d(smem + OFF_QL, &tm, q_full, 3 * D + h * HD, t * QT, b);
+                if (!FAST) tma_load_3d(smem + OFF_QL, &tm, q_full, 3 * D + h * HD, t * QT, b);
             }
+            };
+            if (p.fast) produce(std::true_type{}); else produce(std::false_type{});
         }
     } else if (warp == 11) {
         // ===================== MMA issuer (single thread) =====================
         if (lane == 0) {
+            auto issue = [&](auto fc) {
+            constexpr bool FAST = decltype(fc)::value;
             const uint32_t sb = smem_u32a(smem);
             mbar_wait_a(kv_full, 0);
             if (p.dbg && blockIdx.x == 0) p.dbg[1] = clock64();
@@ -243,7 +251,7 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tm, AttParams p) {
 #pragma unroll
                     for (int k = 0; k < HD / 16; ++k) {
                         const uint64_t ko = (uint64_t)(k * 2);  // +32 B per K=16 step inside the 128 B swizzle row
-                        if (p.fast) { umma_ss(d, qh + ko, kh + ko, IDESC_S, k ? 1u : 0u); continue; }
+                        if (FAST) { umma_ss(d, qh + ko, kh + ko, IDESC_S, k ? 1u : 0u); continue; }
                         umma_ss(d, ql + ko, kh + ko, IDESC_S, k ? 1u : 0u);
                         umma_ss(d, qh + ko, kl + ko, IDESC_S, 1u);
                         umma_ss(d, qh + ko, kh + ko, IDESC_S, 1u);
@@ -264,7 +272,7 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tm, AttParams p) {
                         // the epilogue adds the two 64-column halves.  Measured: three N = 64 MMAs per step ran at ~93 cycles each
                         // (the 4 KB A slice comes from TMEM for every MMA); two MMAs fetch it twice instead of three times.
                         const uint64_t vhl = desc_mnmajor_hilo(sb + OFF_VH + voff + k * 2048), vh = desc_mnmajor(sb + OFF_VH + voff + k * 2048);
-                        if (p.fast) { umma_ts(tmem_base + O_COL, a_hi + k * 8, vh, IDESC_PV, (j | k) ? 1u : 0u); continue; }
+                        if (FAST) { umma_ts(tmem_base + O_COL, a_hi + k * 8, vh, IDESC_PV, (j | k) ? 1u : 0u); continue; }
                         umma_ts(tmem_base + O_COL, a_hi + k * 8, vhl, IDESC_PV2, (j | k) ? 1u : 0u);
                         umma_ts(tmem_base + O_COL, a_lo + k * 8, vh, IDESC_PV, 1u);
                     }
@@ -272,6 +280,8 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tm, AttParams p) {
                 umma_commit_a(o_full);
                 if (p.dbg && blockIdx.x == 0) p.dbg[24 + t] = clock64();
             }
+            };
+            if (p.fast) issue(std::true_type{}); else issue(std::false_type{});
         }
     } else if (warp < 8) {
         // ===================== softmax + epilogue =====================

@@ -31,6 +31,7 @@
 #include <cuda_bf16.h>
 #include <stdlib.h>
 #include <string.h>
+#include <type_traits>
 #include "common.cuh"
 
 namespace {
@@ -799,51 +800,61 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     if (warp == PRODUCER_WARP) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            uint32_t kbc = 0;  // running K-block counter: the ring never drains between tiles
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN_;
-                for (int kb = 0; kb < nkb; ++kb, ++kbc) {
-                    const int s = kbc % NST;
-                    mbar_wait(&empty[s], ((kbc / NST) & 1) ^ 1);
-                    uint8_t* st = smem + s * STAGE_BYTES;
-                    mbar_expect_tx(&full[s], p.fast ? (A_SUB + B_SUB) : STAGE_BYTES);
-                    tma_load_2d(st, &tmA, &full[s], kb * BK, m0);                          // A_hi
-                    if (!p.fast) tma_load_2d(st + A_SUB, &tmA, &full[s], p.Kp + kb * BK, m0);           // A_lo
-                    tma_load_2d(st + 2 * A_SUB, &tmB, &full[s], kb * BK, n0);              // W_hi
-                    if (!p.fast) tma_load_2d(st + 2 * A_SUB + B_SUB, &tmB, &full[s], p.Kp + kb * BK, n0);  // W_lo
+            // FAST (am_set_precision(1)) is resolved ONCE per role: the parity loop carries no extra instruction (measured: a
+            // per-k-step `if (p.fast)` in these single-thread loops cost 4-11 % of the GEMM time)
+            auto produce = [&](auto fc) {
+                constexpr bool FAST = decltype(fc)::value;
+                uint32_t kbc = 0;  // running K-block counter: the ring never drains between tiles
+                for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                    const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN_;
+                    for (int kb = 0; kb < nkb; ++kb, ++kbc) {
+                        const int s = kbc % NST;
+                        mbar_wait(&empty[s], ((kbc / NST) & 1) ^ 1);
+                        uint8_t* st = smem + s * STAGE_BYTES;
+                        mbar_expect_tx(&full[s], FAST ? (A_SUB + B_SUB) : STAGE_BYTES);
+                        tma_load_2d(st, &tmA, &full[s], kb * BK, m0);                          // A_hi
+                        if (!FAST) tma_load_2d(st + A_SUB, &tmA, &full[s], p.Kp + kb * BK, m0);           // A_lo
+                        tma_load_2d(st + 2 * A_SUB, &tmB, &full[s], kb * BK, n0);              // W_hi
+                        if (!FAST) tma_load_2d(st + 2 * A_SUB + B_SUB, &tmB, &full[s], p.Kp + kb * BK, n0);  // W_lo
+                    }
                 }
-            }
+            };
+            if (p.fast) produce(std::true_type{}); else produce(std::false_type{});
         }
     } else if (warp == MMA_WARP) {
         // ===================== MMA issuer (single thread) =====================
         if (lane == 0) {
-            uint32_t kbc = 0;
-            int it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-                const int ab = it & 1;
-                mbar_wait(&tmem_empty[ab], (((it >> 1) & 1) ^ 1));  // epilogue drained this accumulator (first two: free)
-                tc_fence_after();
-                const uint32_t d = tmem_base + (uint32_t)(ab * BN_);
-                for (int kb = 0; kb < nkb; ++kb, ++kbc) {
-                    const int s = kbc % NST;
-                    mbar_wait(&full[s], (kbc / NST) & 1);
+            auto issue = [&](auto fc) {
+                constexpr bool FAST = decltype(fc)::value;
+                uint32_t kbc = 0;
+                int it = 0;
+                for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                    const int ab = it & 1;
+                    mbar_wait(&tmem_empty[ab], (((it >> 1) & 1) ^ 1));  // epilogue drained this accumulator (first two: free)
                     tc_fence_after();
-                    const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
-                    const uint64_t a_hi = make_desc<BK>(base), a_lo = make_desc<BK>(base + A_SUB);
-                    const uint64_t w_hi = make_desc<BK>(base + 2 * A_SUB), w_lo = make_desc<BK>(base + 2 * A_SUB + B_SUB);
+                    const uint32_t d = tmem_base + (uint32_t)(ab * BN_);
+                    for (int kb = 0; kb < nkb; ++kb, ++kbc) {
+                        const int s = kbc % NST;
+                        mbar_wait(&full[s], (kbc / NST) & 1);
+                        tc_fence_after();
+                        const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+                        const uint64_t a_hi = make_desc<BK>(base), a_lo = make_desc<BK>(base + A_SUB);
+                        const uint64_t w_hi = make_desc<BK>(base + 2 * A_SUB), w_lo = make_desc<BK>(base + 2 * A_SUB + B_SUB);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t ko = (uint64_t)(k * 2);
-                        if (p.fast) { umma_bf16(d, a_hi + ko, w_hi + ko, IDESC_P, (kb | k) ? 1u : 0u); continue; }
-                        umma_bf16(d, a_lo + ko, w_hi + ko, IDESC_P, (kb | k) ? 1u : 0u);
-                        umma_bf16(d, a_hi + ko, w_lo + ko, IDESC_P, 1u);
-                        umma_bf16(d, a_hi + ko, w_hi + ko, IDESC_P, 1u);
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint64_t ko = (uint64_t)(k * 2);
+                            if (FAST) { umma_bf16(d, a_hi + ko, w_hi + ko, IDESC_P, (kb | k) ? 1u : 0u); continue; }
+                            umma_bf16(d, a_lo + ko, w_hi + ko, IDESC_P, (kb | k) ? 1u : 0u);
+                            umma_bf16(d, a_hi + ko, w_lo + ko, IDESC_P, 1u);
+                            umma_bf16(d, a_hi + ko, w_hi + ko, IDESC_P, 1u);
+                        }
+                        umma_commit(&empty[s]);
                     }
-                    umma_commit(&empty[s]);
+                    umma_commit(&tmem_full[ab]);
+                    if (dbg && it < 16) p.dbg[8 + it] = clock64();
                 }
-                umma_commit(&tmem_full[ab]);
-                if (dbg && it < 16) p.dbg[8 + it] = clock64();
-            }
+            };
+            if (p.fast) issue(std::true_type{}); else issue(std::false_type{});
         }
     } else if (warp < 8) {
         // ===================== epilogue (overlaps the next tile's main loop) =====================
@@ -1111,6 +1122,8 @@ gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (warp == PRODUCER_WARP) {
         // ===================== TMA producer (both CTAs) =====================
         if (lane == 0) {
+            auto produce = [&](auto fc) {
+            constexpr bool FAST = decltype(fc)::value;
             uint32_t kbc = 0;
             for (int tile = cluster_id; tile < total_items; tile += num_clusters) {
                 int mp, n0; bool narrow;
@@ -1118,7 +1131,7 @@ gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 const int m0 = (mp * 2 + (int)cta_rank) * BM;
                 const int nh = n0 + (int)cta_rank * (narrow ? BN_ / 4 : BN_ / 2);
                 const CUtensorMap* tmW = narrow ? &tmBq : &tmB;
-                const uint32_t stage_tx = p.fast ? (uint32_t)(A_SUB + (narrow ? B_SUB / 2 : B_SUB)) : (uint32_t)(2 * A_SUB + (narrow ? B_SUB : 2 * B_SUB));
+                const uint32_t stage_tx = FAST ? (uint32_t)(A_SUB + (narrow ? B_SUB / 2 : B_SUB)) : (uint32_t)(2 * A_SUB + (narrow ? B_SUB : 2 * B_SUB));
                 for (int kb = 0; kb < nkb; ++kb, ++kbc) {
                     const int s = kbc % NST;
                     mbar_wait(&empty[s], ((kbc / NST) & 1) ^ 1);   // released in both CTAs by the leader's commit multicast
@@ -1130,16 +1143,20 @@ gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" \
                  ::"r"(dst_), "l"(reinterpret_cast<uint64_t>(map_)), "r"(lbar), "r"(c0_), "r"(c1_) : "memory")
                     AM_TMA_2SM(st, &tmA, kb * BK, m0);                               // A_hi (own 128 rows)
-                    if (!p.fast) AM_TMA_2SM(st + A_SUB, &tmA, p.Kp + kb * BK, m0);   // A_lo
+                    if (!FAST) AM_TMA_2SM(st + A_SUB, &tmA, p.Kp + kb * BK, m0);   // A_lo
                     AM_TMA_2SM(st + 2 * A_SUB, tmW, kb * BK, nh);                    // W_hi, own half of the n-tile
-                    if (!p.fast) AM_TMA_2SM(st + 2 * A_SUB + B_SUB, tmW, p.Kp + kb * BK, nh);     // W_lo
+                    if (!FAST) AM_TMA_2SM(st + 2 * A_SUB + B_SUB, tmW, p.Kp + kb * BK, nh);     // W_lo
 #undef AM_TMA_2SM
                 }
             }
+            };
+            if (p.fast) produce(std::true_type{}); else produce(std::false_type{});
         }
     } else if (warp == MMA_WARP) {
         // ===================== MMA issuer: one thread of the LEADER CTA for the pair =====================
         if (lane == 0 && leader) {
+            auto issue = [&](auto fc) {
+            constexpr bool FAST = decltype(fc)::value;
             uint32_t kbc = 0;
             int it = 0;
             for (int tile = cluster_id; tile < total_items; tile += num_clusters, ++it) {
@@ -1161,7 +1178,7 @@ gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #define AM_UMMA_2SM(a_, b_, acc_)                                                                                     \
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" \
                  ::"r"(d), "l"(a_), "l"(b_), "r"(idesc), "r"((uint32_t)(acc_)) : "memory")
-                        if (p.fast) { AM_UMMA_2SM(a_hi + ko, w_hi + ko, (kb | k) ? 1u : 0u); continue; }
+                        if (FAST) { AM_UMMA_2SM(a_hi + ko, w_hi + ko, (kb | k) ? 1u : 0u); continue; }
                         AM_UMMA_2SM(a_lo + ko, w_hi + ko, (kb | k) ? 1u : 0u);
                         AM_UMMA_2SM(a_hi + ko, w_lo + ko, 1u);
                         AM_UMMA_2SM(a_hi + ko, w_hi + ko, 1u);
@@ -1174,6 +1191,8 @@ gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                              ::"r"(smem_u32(&tmem_full[ab])), "h"((uint16_t)3) : "memory");
                 if (dbg && it < 16) p.dbg[8 + it] = clock64();
             }
+            };
+            if (p.fast) issue(std::true_type{}); else issue(std::false_type{});
         }
     } else if (warp < 8) {
         // ===================== epilogue (both CTAs: own 128 x BN accumulator) =====================
