@@ -96,7 +96,8 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         med = lambda v: sorted(v)[len(v) // 2] if v else None
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm),
+        head = by_phase.get("resident", []) + by_phase.get("e2e", [])  # the headline's timed regions (the extra legs are listed per phase)
+        return {"sm_mhz": med(head) if head else med(sm), "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm),
                 "sm_mhz_min": sm[0] if sm else None, "power_w_max": max(pw) if pw else None,
                 "sm_mhz_by_phase": {k: {"median": med(v), "min": min(v), "n": len(v)} for k, v in by_phase.items()}}
 
