@@ -261,27 +261,26 @@ class BatchNormTrainFn(Function):
         acc = torch.zeros(2 * C + 1, dtype=torch.float64, device=dev)
         mean, invstd, var = (torch.empty(C, device=dev) for _ in range(3))
         cnt = None
+        _l.check(L().am_bn_train_stats(_p(x), M, C, float(bn.eps), _p(acc), _p(mean), _p(invstd), _p(var), _st()), "am_bn_train_stats")
         if sync:
             # global statistics: (sum, sumsq, row count) over all ranks in ONE all-reduce; the count stays on the device — a
             # host read here (.item()) would drain the GPU once per BatchNorm layer, 28 times per CMDM training step
-            _l.check(L().am_bn_train_stats(_p(x), M, C, float(bn.eps), _p(acc), _p(mean), _p(invstd), _p(var), _st()), "am_bn_train_stats")
             acc[2 * C:].fill_(float(M))
             dist.all_reduce(acc)
             cnt = acc[2 * C:]
-            mu = acc[:C] / cnt
-            v = (acc[C:2 * C] / cnt - mu * mu).clamp_min(0)
-            mean, var, invstd = mu.float(), v.float(), (1.0 / torch.sqrt(v + bn.eps)).float()
-        else:
-            _l.check(L().am_bn_train_stats(_p(x), M, C, float(bn.eps), _p(acc), _p(mean), _p(invstd), _p(var), _st()), "am_bn_train_stats")
+        track = bn.track_running_stats and bn.running_mean is not None
+        if sync or track:
+            # finalise (mean / invstd / var from the global sums) + running-statistics update in ONE launch (torch semantics:
+            # unbiased variance, momentum); under SyncBatchNorm this replaces ~8 tiny launches behind every all-reduce
+            mom = bn.momentum if bn.momentum is not None else 0.1
+            with torch.no_grad():
+                _l.check(L().am_bn_finalize_running(_p(acc), _p(cnt) if sync else None, M, C, float(bn.eps), _p(mean), _p(invstd), _p(var),
+                                                    _p(bn.running_mean) if track else None, _p(bn.running_var) if track else None, float(mom),
+                                                    _p(bn.num_batches_tracked) if track else None, _st()), "am_bn_finalize_running")
+                if track:  # the kernel wrote the buffers behind torch's back: bump their version counters (amb200.pack.params_version)
+                    torch.autograd.graph.increment_version([bn.running_mean, bn.running_var, bn.num_batches_tracked])
         y = torch.empty_like(x)
         _l.check(L().am_bn_apply(_p(x), _p(mean), _p(invstd), _p(gamma), _p(beta), _p(y), M, C, int(relu), _st()), "am_bn_apply")
-        if bn.track_running_stats and bn.running_mean is not None:  # torch semantics: unbiased variance, momentum update
-            with torch.no_grad():
-                mom = bn.momentum if bn.momentum is not None else 0.1
-                bn.running_mean.mul_(1 - mom).add_(mean, alpha=mom)
-                unbias = (cnt / (cnt - 1).clamp_min(1)).float() if sync else M / max(M - 1, 1)
-                bn.running_var.mul_(1 - mom).add_(var * unbias, alpha=mom)
-                bn.num_batches_tracked += 1
         ctx.save_for_backward(x, y if relu else x, mean, invstd, gamma)
         ctx.relu, ctx.sync, ctx.cnt = relu, sync, cnt
         return y

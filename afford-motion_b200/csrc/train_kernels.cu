@@ -543,6 +543,38 @@ extern "C" int am_bn_train_stats(const float* X, int M, int C, float eps, double
     AM_LAUNCH_CHECK("bn_finalize");
     return AM_OK;
 }
+// Statistics finalisation + running-statistics update in ONE launch (was ~8 tiny ATen launches per BatchNorm layer per step, 28
+// layers per CMDM training step; under SyncBatchNorm they sat on the critical path right behind each all-reduce).
+//   acc[2C] = (sum x, sum x^2) over `cnt` rows; cnt = *cnt_dev (SyncBatchNorm: the all-reduced global row count, acc[2C]) or M.
+//   mean / invstd / biased var as torch.nn.functional.batch_norm(training=True); running stats with the unbiased variance and
+//   `momentum` (torch semantics); num_batches_tracked += 1.
+__global__ void bn_finalize_running_kernel(const double* __restrict__ acc, const double* __restrict__ cnt_dev, int M, int C, float eps,
+                                           float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ var_biased,
+                                           float* __restrict__ run_mean, float* __restrict__ run_var, float momentum,
+                                           long long* __restrict__ nbt) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && nbt) *nbt += 1;
+    if (c >= C) return;
+    const double cnt = cnt_dev ? *cnt_dev : (double)M;
+    const double mu = acc[c] / cnt;
+    double var = acc[C + c] / cnt - mu * mu;
+    if (var < 0) var = 0;
+    mean[c] = (float)mu; var_biased[c] = (float)var; invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (run_mean && run_var) {
+        const double unbias = cnt / (cnt - 1.0 > 1.0 ? cnt - 1.0 : 1.0);
+        run_mean[c] = (1.0f - momentum) * run_mean[c] + momentum * (float)mu;
+        run_var[c] = (1.0f - momentum) * run_var[c] + momentum * (float)((float)var * (float)unbias);
+    }
+}
+extern "C" int am_bn_finalize_running(const double* acc, const double* cnt_dev, int M, int C, float eps, float* mean, float* invstd,
+                                      float* var_biased, float* run_mean, float* run_var, float momentum, int64_t* num_batches_tracked,
+                                      am_stream_t stream) {
+    AM_REQUIRE(acc && mean && invstd && var_biased && C > 0 && (cnt_dev || M > 0), AM_EINVAL, "am_bn_finalize_running: bad args");
+    bn_finalize_running_kernel<<<cdiv(C, 128), 128, 0, ST>>>(acc, cnt_dev, M, C, eps, mean, invstd, var_biased, run_mean, run_var, momentum,
+                                                            reinterpret_cast<long long*>(num_batches_tracked));
+    AM_LAUNCH_CHECK("bn_finalize_running");
+    return AM_OK;
+}
 extern "C" int am_bn_apply(const float* X, const float* mean, const float* invstd, const float* gamma, const float* beta, float* Y, int M, int C, int relu,
                            am_stream_t stream) {
     AM_REQUIRE(X && mean && invstd && gamma && beta && Y && M > 0 && C > 0, AM_EINVAL, "am_bn_apply: bad args");

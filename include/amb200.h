@@ -299,6 +299,12 @@ int am_softmax_rows_bwd(float* dP, const float* P, int rows, int Sk, float scale
 /* BatchNorm1d over the M rows of X [M,C]: acc = caller-zeroed [2C] double scratch */
 int am_bn_train_stats(const float* X, int M, int C, float eps, double* acc, float* mean, float* invstd, float* var_biased,
                       am_stream_t stream);
+/* statistics finalisation + running-statistics update (momentum, unbiased variance, num_batches_tracked += 1: torch
+ * BatchNorm1d training semantics, pointtransformer.py BatchNorm1d layers) in one launch.  acc [2C] = (sum x, sum x^2) over cnt
+ * rows, cnt = *cnt_dev (SyncBatchNorm: the all-reduced global row count) or M when cnt_dev is NULL.  run_* / nbt may be NULL. */
+int am_bn_finalize_running(const double* acc, const double* cnt_dev, int M, int C, float eps, float* mean, float* invstd,
+                           float* var_biased, float* run_mean, float* run_var, float momentum, int64_t* num_batches_tracked,
+                           am_stream_t stream);
 int am_bn_apply(const float* X, const float* mean, const float* invstd, const float* gamma, const float* beta, float* Y,
                 int M, int C, int relu, am_stream_t stream);
 int am_bn_bwd(const float* dY, const float* X, const float* Y, const float* mean, const float* invstd, const float* gamma,
