@@ -42,6 +42,8 @@ class CMDMEngine:
         assert self.gemm in ("tc", "simt")
         # "tc": tcgen05 attention (default with the tc GEMM path, S <= 384); "simt": fp32 SIMT attention kernel
         self.attn = os.environ.get("AMB200_ATTN", "tc")
+        # out_proj / linear2 + residual + LayerNorm as one tcgen05 kernel (csrc/gemm_ln_tc.cu); AMB200_LN_FUSE=0: separate GEMM + LayerNorm
+        self.fuse_ln = os.environ.get("AMB200_LN_FUSE", "1") != "0"
         assert self.attn in ("tc", "simt")
 
     # ------------------------------------------------------------------ weights
@@ -224,6 +226,7 @@ class CMDMEngine:
                       residual=w["pe"][2 + G:2 + G + T], ldr=D, res_mod=T, ymap=(T, S, 2 + G), ldy=D, Np2=D)
         cur, curS = X0.view(M, D), X0S
         ffp = ops.pad32(self.ff)
+        fuse_ln = self.fuse_ln and D == 512 and ffp % 64 == 0
         for i in range(self.nlayers):
             p = f"l{i}."
             last = i == self.nlayers - 1
@@ -236,11 +239,18 @@ class CMDMEngine:
                 ops.mha_fwd(ws["QKV"], None, cond.key_pad, B, S, H, hd, 1.0 / math.sqrt(hd), out2=ws["ATTS"])
             # residual streams travel as the bf16 (hi|lo) pairs the LayerNorm / adapter epilogues already write for the next
             # GEMM's A operand (x = hi + lo, 16 significant bits): no fp32 copy of the activations is written at all
-            ops.linear_tc(ws["ATTS"], w[p + "out_w2"], M, D, D, y=ws["TMP"], bias=w[p + "out_b"], residual_split=curS)
-            ops.layernorm(ws["TMP"], w[p + "n1g"], w[p + "n1b"], None, M, D, eps=w[p + "eps1"], y2=ws["Y1S"])
-            ops.linear_tc(ws["Y1S"], w[p + "w12"], M, self.ff, D, y2=ws["FFS"], bias=w[p + "b1"], act="gelu", Np2=ffp)
-            ops.linear_tc(ws["FFS"], w[p + "w22"], M, D, ffp, y=ws["TMP"], bias=w[p + "b2"], residual_split=ws["Y1S"])
-            ops.layernorm(ws["TMP"], w[p + "n2g"], w[p + "n2b"], None, M, D, eps=w[p + "eps2"], y2=nxtS)
+            if fuse_ln:
+                # out_proj + residual + norm1 and linear2 + residual + norm2 as ONE tcgen05 kernel each: the full 512-column row sits in
+                # the CTA pair's tensor memory, the fp32 hand-off tensor and the LayerNorm launch disappear (csrc/gemm_ln_tc.cu)
+                ops.linear_ln_tc(ws["ATTS"], w[p + "out_w2"], M, D, D, w[p + "out_b"], curS, w[p + "n1g"], w[p + "n1b"], w[p + "eps1"], ws["Y1S"])
+                ops.linear_tc(ws["Y1S"], w[p + "w12"], M, self.ff, D, y2=ws["FFS"], bias=w[p + "b1"], act="gelu", Np2=ffp)
+                ops.linear_ln_tc(ws["FFS"], w[p + "w22"], M, D, ffp, w[p + "b2"], ws["Y1S"], w[p + "n2g"], w[p + "n2b"], w[p + "eps2"], nxtS)
+            else:
+                ops.linear_tc(ws["ATTS"], w[p + "out_w2"], M, D, D, y=ws["TMP"], bias=w[p + "out_b"], residual_split=curS)
+                ops.layernorm(ws["TMP"], w[p + "n1g"], w[p + "n1b"], None, M, D, eps=w[p + "eps1"], y2=ws["Y1S"])
+                ops.linear_tc(ws["Y1S"], w[p + "w12"], M, self.ff, D, y2=ws["FFS"], bias=w[p + "b1"], act="gelu", Np2=ffp)
+                ops.linear_tc(ws["FFS"], w[p + "w22"], M, D, ffp, y=ws["TMP"], bias=w[p + "b2"], residual_split=ws["Y1S"])
+                ops.layernorm(ws["TMP"], w[p + "n2g"], w[p + "n2b"], None, M, D, eps=w[p + "eps2"], y2=nxtS)
             cur, curS = nxt, nxtS
         if out is None:
             out = torch.empty(B, T, Dm, device=x.device)

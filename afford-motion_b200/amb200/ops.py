@@ -264,6 +264,14 @@ def linear_tc(a2, w2, M, N, Kp, y=None, y2=None, bias=None, act=None, residual=N
     return y if y is not None else y2
 
 
+def linear_ln_tc(a2, w2, M, N, Kp, bias, residual_split, gamma, beta, eps, y2):
+    """y2 = split(LayerNorm(a w^T + bias + residual)) in one tcgen05 kernel (see am_linear_ln_tc; N must be 512)."""
+    _chk_cuda(a2, w2, residual_split, y2)
+    _l.check(_l.load().am_linear_ln_tc(_ptr(a2), _ptr(w2), M, N, Kp, _ptr(bias), _ptr(residual_split), residual_split.shape[-1] // 2,
+                                      _ptr(gamma), _ptr(beta), float(eps), _ptr(y2), _stream()), "am_linear_ln_tc")
+    return y2
+
+
 # ------------------------------------------------------------------ optional per-kernel CUDA-event profiler (bench.py)
 class KernelProfiler:
     """Records a CUDA event pair around every op wrapper call on the launching (current torch) stream.
@@ -290,7 +298,7 @@ def _flops_of(name, args, kwargs):
     if name == "linear":
         M, N, K = args[3], args[4], args[5]
         return 2.0 * M * N * K
-    if name == "linear_tc":
+    if name in ("linear_tc", "linear_ln_tc"):
         return 2.0 * args[2] * args[3] * args[4]
     if name == "mha_tc_fwd":
         B, S, H, hd = args[4], args[5], args[6], args[7]
@@ -320,5 +328,5 @@ def _wrap(name, fn):
 for _n in ("randn_", "p_sample_update", "ddim_update", "q_sample", "masked_mse", "add_i32", "linear", "linear_batched", "layernorm", "mha_fwd",
            "gather_time_token", "gather_rows", "furthestsampling", "knnquery", "pt_layer_fwd", "transition_down_fwd", "interpolation", "segment_mean",
            "cdm_encoder_partial", "cdm_encoder_combine", "cdm_decoder_point", "cdm_enc_points", "cdm_enc_expand", "cdm_dec_prep",
-           "cdm_dec_points_tc", "cdm_latent_pre", "cdm_latent_post", "linear_skinny", "split_bf16", "linear_tc", "mha_tc_fwd"):
+           "cdm_dec_points_tc", "cdm_latent_pre", "cdm_latent_post", "linear_ln_tc", "linear_skinny", "split_bf16", "linear_tc", "mha_tc_fwd"):
     globals()[_n] = _wrap(_n, globals()[_n])

@@ -264,6 +264,14 @@ int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp, const flo
                  const float* residual, int ldr, int res_mod, float* Y, int ldy, int yin_g, int yout_g, int y_off,
                  void* Y2, int Np2, am_stream_t stream);
 
+/* GEMM + residual + LayerNorm in one tcgen05 kernel (N = 512 only: the whole output row lives in one CTA's tensor memory):
+ *   Y2 [M, 2*512] bf16 (hi|lo) = split( LayerNorm( A W^T + bias + (R_hi + R_lo) ; gamma, beta, eps ) )
+ * A2 [M, 2*Kp], W2 [512, 2*Kp], R2 [M, 2*ldr] bf16 (hi|lo) as in am_linear_tc; Kp % 64 == 0.  Replaces out_proj + norm1 and
+ * linear2 + norm2 of torch.nn.TransformerEncoderLayer (post-LN, models/cmdm.py:66-77) — the fp32 hand-off tensor between
+ * am_linear_tc and am_layernorm and one launch per LayerNorm disappear.  Honours am_set_precision. */
+int am_linear_ln_tc(const void* A2, const void* W2, int M, int N, int Kp, const float* bias, const void* R2, int ldr,
+                    const float* gamma, const float* beta, float eps, void* Y2, am_stream_t stream);
+
 /* tcgen05 multi-head self-attention (S <= 384, head dim 64): softmax(q k^T * scale + key mask) v per (batch, head),
  * fp32-equivalent accuracy (3-term bf16 split, fp32 TMEM accumulation, exact softmax — the whole key row lives in TMEM,
  * P is fed to the PV MMA straight from TMEM).  qkv2 [B*S, 2*3*H*64] bf16 = (hi | lo) x (q|k|v) as written by the in_proj

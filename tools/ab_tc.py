@@ -30,6 +30,9 @@ ks = {
     "ffn1     [10432x1024x512]": lambda: ops.linear_tc(y1s, w1s, M, FF, D, y2=ffs, bias=biasf, act="gelu", Np2=FF),
     "ffn2     [10432x512x1024]": lambda: ops.linear_tc(ffs, w2s, M, D, FF, y=tmp, bias=bias1, residual_split=y1s),
 }
+if hasattr(lib.load(), "am_linear_ln_tc"):
+    ks["out_proj+LN fused        "] = lambda: ops.linear_ln_tc(atts, wouts, M, D, D, bias1, xs, gam, bet, 1e-5, y1s)
+    ks["ffn2+LN fused            "] = lambda: ops.linear_ln_tc(ffs, w2s, M, D, FF, bias1, y1s, gam, bet, 1e-5, atts)
 print("library:", lib.LIB_PATH)
 for _ in range(3):
     for f in ks.values():
@@ -46,6 +49,6 @@ for name, f in ks.items():
     e.record()
     torch.cuda.synchronize()
     us = 1e3 * s.elapsed_time(e) / reps
-    tot += us * (2 if "layernorm" in name else 1)
+    tot += 0.0 if "fused" in name else us * (2 if "layernorm" in name else 1)
     print(f"  {name} {us:8.2f} us")
 print(f"  layer total (2 LN) {tot:8.2f} us -> x5 layers {5 * tot / 1e3:.3f} ms")
