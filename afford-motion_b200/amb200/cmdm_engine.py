@@ -42,8 +42,10 @@ class CMDMEngine:
         assert self.gemm in ("tc", "simt")
         # "tc": tcgen05 attention (default with the tc GEMM path, S <= 384); "simt": fp32 SIMT attention kernel
         self.attn = os.environ.get("AMB200_ATTN", "tc")
-        # out_proj / linear2 + residual + LayerNorm as one tcgen05 kernel (csrc/gemm_ln_tc.cu); AMB200_LN_FUSE=0: separate GEMM + LayerNorm
-        self.fuse_ln = os.environ.get("AMB200_LN_FUSE", "1") != "0"
+        # AMB200_LN_FUSE=1: out_proj / linear2 + residual + LayerNorm as one tcgen05 kernel (csrc/gemm_ln_tc.cu).  OFF by default:
+        # measured 44.3 / 58.9 us against 34.1 / 42.8 us for GEMM + LayerNorm (profiles/r2_gemm_ln_fused_ab.txt) — its row-per-lane
+        # epilogue is bound by uncoalesced residual / output accesses; parity-tested, kept for the next round
+        self.fuse_ln = os.environ.get("AMB200_LN_FUSE", "0") == "1"
         assert self.attn in ("tc", "simt")
 
     # ------------------------------------------------------------------ weights
