@@ -153,7 +153,7 @@ class CMDMEngine:
             if self.gemm == "tc":
                 bf = lambda r, c: torch.zeros(r, c, dtype=torch.bfloat16, device=dev)
                 ws.update({"X0S": bf(M, 2 * D), "XSa": bf(M, 2 * D), "XSb": bf(M, 2 * D), "ATTS": bf(M, 2 * D), "Y1S": bf(M, 2 * D),
-                           "FFS": bf(M, 2 * ops.pad32(ff)), "xS": None, "QKVS": bf(M, 6 * D)})
+                           "FFS": bf(M, 2 * ops.pad32(ff)), "xS": bf(B * T, 2 * ops.pad32(self.m.motion_dim)), "QKVS": bf(M, 6 * D)})
             self._ws[key] = ws
         return ws
 
@@ -171,8 +171,10 @@ class CMDMEngine:
     # ------------------------------------------------------------------ one network evaluation
     @torch.no_grad()
     def forward(self, x: torch.Tensor, t_dev: torch.Tensor, t_stride: int, cond: CMDMCondition, out: Optional[torch.Tensor] = None,
-                time_table: Optional[torch.Tensor] = None):
-        """x [B,T,Dm] fp32 contiguous, t_dev int32 device ([1] shared or [B]) -> x0_hat [B,T,Dm]."""
+                time_table: Optional[torch.Tensor] = None, prologue: bool = True):
+        """x [B,T,Dm] fp32 contiguous, t_dev int32 device ([1] shared or [B]) -> x0_hat [B,T,Dm].
+        prologue=False (device-resident sampling loop, tc path): the time token of this timestep and the bf16 split of x were already
+        written by the previous step's fused sampler update (am_p_sample_update_next) or by `step_prologue` at the start of the job."""
         self.refresh()
         w, m = self.w, self.m
         B, T, Dm = x.shape
@@ -183,7 +185,7 @@ class CMDMEngine:
         self.bind_condition(ws, cond)
         X0 = ws["X0"]
         if self.gemm == "tc":
-            return self._forward_tc(x, t_dev, t_stride, cond, out, time_table, ws)
+            return self._forward_tc(x, t_dev, t_stride, cond, out, time_table, ws, prologue)
         ops.gather_time_token(X0, S, D, 0, w["time_table"] if time_table is None else time_table, t_dev, t_stride, B)
         # motion tokens + PE[2+G+j] -> rows 2+G.. of every sample   (cmdm.py:159-162)
         ops.linear(x, w["motion_adapter.w"], X0, B * T, D, Dm, bias=w["motion_adapter.b"], residual=w["pe"][2 + G:2 + G + T], ldr=D,
@@ -207,7 +209,14 @@ class CMDMEngine:
         ops.linear(cur, w["motion_layer.w"], out, B * T, Dm, D, bias=w["motion_layer.b"], xmap=(T, S, 2 + G))
         return out
 
-    def _forward_tc(self, x, t_dev, t_stride, cond, out, time_table, ws):
+    def step_prologue(self, x, t_dev, t_stride, ws, time_table=None):
+        """Time token of the current timestep into row 0 of every sample + bf16 (hi|lo) split of x (A operand of the motion adapter)."""
+        B, T, Dm = x.shape
+        S, D = ws["X0"].shape[1], self.m.latent_dim
+        ops.gather_time_token(ws["X0"], S, D, 0, self.w["time_table"] if time_table is None else time_table, t_dev, t_stride, B, x2=ws["X0S"])
+        ops.split_bf16(x, B * T, Dm, out=ws["xS"])
+
+    def _forward_tc(self, x, t_dev, t_stride, cond, out, time_table, ws, prologue=True):
         """Same network evaluation with every large GEMM on the tcgen05 path (3-term bf16 split, fp32 accumulate):
         activations travel between GEMMs as bf16 (hi|lo) pairs written by the producing kernel's epilogue
         (GEMM / LayerNorm / attention), fp32 copies are kept only where a residual or the attention kernel needs them."""
@@ -219,11 +228,9 @@ class CMDMEngine:
         H = self.nhead
         hd = D // H
         X0, X0S = ws["X0"], ws["X0S"]
-        ops.gather_time_token(X0, S, D, 0, w["time_table"] if time_table is None else time_table, t_dev, t_stride, B, x2=X0S)
         Kx = ops.pad32(Dm)
-        if ws["xS"] is None or ws["xS"].shape[0] != B * T:
-            ws["xS"] = torch.zeros(B * T, 2 * Kx, dtype=torch.bfloat16, device=x.device)
-        ops.split_bf16(x, B * T, Dm, out=ws["xS"])
+        if prologue:
+            self.step_prologue(x, t_dev, t_stride, ws, time_table)
         ops.linear_tc(ws["xS"], w["motion_adapter.w2"], B * T, D, Kx, y=None, y2=X0S, bias=w["motion_adapter.b"],
                       residual=w["pe"][2 + G:2 + G + T], ldr=D, res_mod=T, ymap=(T, S, 2 + G), ldy=D, Np2=D)
         cur, curS = X0.view(M, D), X0S

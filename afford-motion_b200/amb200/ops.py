@@ -34,10 +34,18 @@ def randn_(out: torch.Tensor, per_sample: int, nsample: int, sample0: int, seed:
     return out
 
 
-def p_sample_update(x0_hat, x_t, x_prev, noise, coef1, coef2, logvar, t, t_stride, seed=0, sample0=0, seed_dev=None):
+def p_sample_update(x0_hat, x_t, x_prev, noise, coef1, coef2, logvar, t, t_stride, seed=0, sample0=0, seed_dev=None, nxt=None):
+    """nxt (optional, CMDM sampling loop): dict(xs2, D, Kx, tokX, tokX2, S, TD, table) — the update also writes the next denoise
+    step's prologue (bf16 split of x_prev, time token of t-1), see am_p_sample_update_next."""
     _chk_cuda(x0_hat, x_t, x_prev, t)
     B = x_t.shape[0]
     per = x_t.numel() // B
+    if nxt is not None:
+        _l.check(_l.load().am_p_sample_update_next(_ptr(_f32c(x0_hat)), _ptr(_f32c(x_t)), _ptr(x_prev), _ptr(noise), _ptr(coef1), _ptr(coef2),
+                                                  _ptr(logvar), _ptr(t), t_stride, B, per, seed, _ptr(seed_dev), sample0, _ptr(nxt["xs2"]), nxt["D"],
+                                                  nxt["Kx"], _ptr(nxt["tokX"]), _ptr(nxt["tokX2"]), nxt["S"], nxt["TD"], _ptr(nxt["table"]), _stream()),
+                 "am_p_sample_update_next")
+        return x_prev
     _l.check(_l.load().am_p_sample_update(_ptr(_f32c(x0_hat)), _ptr(_f32c(x_t)), _ptr(x_prev), _ptr(noise), _ptr(coef1), _ptr(coef2),
                                          _ptr(logvar), _ptr(t), t_stride, B, per, seed, _ptr(seed_dev), sample0, _stream()), "am_p_sample_update")
     return x_prev

@@ -321,12 +321,21 @@ class GaussianDiffusion:
             t_dev.fill_(n - 1)
             seed_dev.fill_(int(seed))
 
+            # CMDM (tc path), ancestral sampling: the sampler update also writes the NEXT step's prologue (bf16 split of x_{t-1}, time
+            # token of t-1), so a step is network evaluation + ONE elementwise launch; the first step's prologue runs once per job
+            nxt = handle.fuse_next() if (kind == "ddpm" and hasattr(handle, "fuse_next")) else None
+            if nxt is not None:
+                handle.prepare(img, t_dev)
+
             def one_step(nz=None):
                 with _nvtx("network_eval"):
-                    handle.forward(img, t_dev, x0)
+                    if nxt is not None:
+                        handle.forward(img, t_dev, x0, prologue=False)
+                    else:
+                        handle.forward(img, t_dev, x0)
                 if kind == "ddpm":
                     ops.p_sample_update(x0, img, img, nz, tab["coef1"], tab["coef2"], tab["logvar"], t_dev, 0, seed_dev=seed_dev,
-                                        sample0=self.sample_offset)
+                                        sample0=self.sample_offset, nxt=nxt)
                 else:
                     ops.ddim_update(x0, img, img, nz, tab["sqrt_recip_ac"], tab["sqrt_recipm1_ac"], tab["ac"], tab["ac_prev"], eta,
                                     t_dev, 0, seed_dev=seed_dev, sample0=self.sample_offset)

@@ -176,5 +176,22 @@ class _CMDMSamplerHandle:
         self.cond.static_tokens = cond.static_tokens
         ws["cond_id"] = self.cond
 
-    def forward(self, x, t_dev, out):
-        return self.eng.forward(x, t_dev, 0, self.cond, out=out, time_table=self.table)
+    def forward(self, x, t_dev, out, prologue=True):
+        return self.eng.forward(x, t_dev, 0, self.cond, out=out, time_table=self.table, prologue=prologue)
+
+    def _ws(self):
+        c = self.cond
+        return self.eng.workspace(c.B, c.G, c.T, c.static_tokens.device)
+
+    def fuse_next(self):
+        """Buffers the fused sampler update writes for the next step (ops.p_sample_update(nxt=...)); None on the SIMT GEMM path."""
+        if self.eng.gemm != "tc":
+            return None
+        from amb200 import ops
+        ws, m = self._ws(), self.eng.m
+        return dict(xs2=ws["xS"], D=m.motion_dim, Kx=ops.pad32(m.motion_dim), tokX=ws["X0"], tokX2=ws["X0S"], S=ws["X0"].shape[1],
+                    TD=m.latent_dim, table=self.table)
+
+    def prepare(self, x, t_dev):
+        """Once per job, before the first step: what every later step gets from the previous step's fused update."""
+        self.eng.step_prologue(x, t_dev, 0, self._ws(), self.table)
