@@ -25,47 +25,59 @@ struct GemmG {
     int ksplit, kchunk;  // ksplit > 1 (batch == 1 only): blockIdx.z owns K range [z*kchunk, ...), results are atomically added into C
 };
 
-// 64 x 64 tile, BK = 16, 4 x 4 accumulators per thread.  Round 2: operand tiles double-buffered in shared memory with the next
-// tile's global loads in flight during the FMAs, and 128-bit shared-memory reads (2 LDS.128 per 16 FMAs; the round-1 kernel issued 8
-// scalar LDS per 16 FMAs and ran the training step's batched attention GEMMs at ~11 TFLOP/s).
+// BM x 64 tile (BM = 64: 4 x 4 accumulators per thread; BM = 128: 8 x 4), BK = 16.  Round 2: operand tiles double-buffered in shared
+// memory with the next tile's global loads in flight during the FMAs, and 128-bit shared-memory reads (BM = 128: 3 LDS.128 per 32
+// FMAs; the round-1 kernel issued 8 scalar LDS per 16 FMAs and ran the training step's batched attention GEMMs at ~11 TFLOP/s).
+template <int BM>
 __global__ void __launch_bounds__(256) gemm_general_kernel(GemmG g) {
-    constexpr int BT = 64, BK = 16, LD = BT + 4;  // row stride 68 floats: rows stay 16-byte aligned
-    __shared__ __align__(16) float As[2][BK][LD];
-    __shared__ __align__(16) float Bs[2][BK][LD];
+    constexpr int BT = 64, BK = 16, LDA = BM + 4, LDB = BT + 4;  // row strides keep 16-byte alignment
+    constexpr int TM = BM / 16;            // accumulator rows per thread
+    constexpr int SA = BM * BK / 256;      // A elements staged per thread per k-tile
+    __shared__ __align__(16) float As[2][BK][LDA];
+    __shared__ __align__(16) float Bs[2][BK][LDB];
     const int bi = g.ksplit > 1 ? 0 : blockIdx.z;
     const int kbeg = g.ksplit > 1 ? blockIdx.z * g.kchunk : 0;
     const int kend = g.ksplit > 1 ? min(g.K, kbeg + g.kchunk) : g.K;
     const float* A = g.A + (bi / g.bdiv) * g.sA1 + (bi % g.bdiv) * g.sA2;
     const float* B = g.B + (bi / g.bdiv) * g.sB1 + (bi % g.bdiv) * g.sB2;
     float* C = g.C + (bi / g.bdiv) * g.sC1 + (bi % g.bdiv) * g.sC2;
-    const int m0 = blockIdx.y * BT, n0 = blockIdx.x * BT;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BT;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    float acc[4][4];
+    float acc[TM][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < TM; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    // element (m, k) / (k, n) this thread stages for each of its 4 slots (depends only on the transposition flags)
-    int am[4], ak[4], bn[4], bk[4];
+    // element (m, k) / (k, n) this thread stages in each of its slots (depends only on the transposition flags)
+    int am[SA], ak[SA], bn[4], bk[4];
+#pragma unroll
+    for (int i = 0; i < SA; ++i) {
+        const int idx = tid + i * 256;
+        if (g.transA) { am[i] = idx % BM; ak[i] = idx / BM; } else { ak[i] = idx & 15; am[i] = idx >> 4; }
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int idx = tid + i * 256;
-        if (g.transA) { am[i] = idx & 63; ak[i] = idx >> 6; } else { ak[i] = idx & 15; am[i] = idx >> 4; }
         if (g.transB) { bk[i] = idx & 15; bn[i] = idx >> 4; } else { bn[i] = idx & 63; bk[i] = idx >> 6; }
     }
-    float ra[4], rb[4];
+    float ra[SA], rb[4];
     auto load_tile = [&](int k0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < SA; ++i) {
             const int gm = m0 + am[i], gka = k0 + ak[i];
             ra[i] = (gm < g.M && gka < kend) ? (g.transA ? A[(int64_t)gka * g.lda + gm] : A[(int64_t)gm * g.lda + gka]) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
             const int gn = n0 + bn[i], gkb = k0 + bk[i];
             rb[i] = (gn < g.N && gkb < kend) ? (g.transB ? B[(int64_t)gn * g.ldb + gkb] : B[(int64_t)gkb * g.ldb + gn]) : 0.f;
         }
     };
     auto store_tile = [&](int buf) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { As[buf][ak[i]][am[i]] = ra[i]; Bs[buf][bk[i]][bn[i]] = rb[i]; }
+        for (int i = 0; i < SA; ++i) As[buf][ak[i]][am[i]] = ra[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) Bs[buf][bk[i]][bn[i]] = rb[i];
     };
     load_tile(kbeg);
     store_tile(0);
@@ -76,11 +88,16 @@ __global__ void __launch_bounds__(256) gemm_general_kernel(GemmG g) {
         if (more) load_tile(k0 + BK);  // global loads of the next tile overlap the FMAs below
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
-            const float4 a4 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
-            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
-            const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+            float a[TM];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < TM; i += 4) {
+                const float4 a4 = *reinterpret_cast<const float4*>(&As[buf][k][ty * TM + i]);
+                a[i] = a4.x; a[i + 1] = a4.y; a[i + 2] = a4.z; a[i + 3] = a4.w;
+            }
+            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+            const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         }
@@ -88,8 +105,8 @@ __global__ void __launch_bounds__(256) gemm_general_kernel(GemmG g) {
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        int m = m0 + ty * 4 + i;
+    for (int i = 0; i < TM; ++i) {
+        int m = m0 + ty * TM + i;
         if (m >= g.M) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -479,7 +496,9 @@ extern "C" int am_gemm_f32(int transA, int transB, int M, int N, int K, float al
         }
     }
     GemmG g{A, B, C, M, N, K, lda, ldb, ldc, transA, transB, alpha, beta, bdiv, sA1, sA2, sB1, sB2, sC1, sC2, 1, K};
-    dim3 grid(cdiv(N, 64), cdiv(M, 64), batch);
+    // 128-row tiles (8 x 4 accumulators per thread) when that still leaves >= 2 waves of CTAs, else 64-row tiles
+    const bool big = M >= 128 && (int64_t)cdiv(N, 64) * cdiv(M, 128) * batch >= 2 * AM_NUM_SMS;
+    dim3 grid(cdiv(N, 64), cdiv(M, big ? 128 : 64), batch);
     // split-K for deep reductions with few output tiles (weight gradients dW = dY^T X: K = rows of the batch)
     const int64_t tiles = (int64_t)grid.x * grid.y;
     if (batch == 1 && beta == 0.f && ldc == N && K >= 2048 && tiles < 2 * AM_NUM_SMS) {
@@ -493,7 +512,8 @@ extern "C" int am_gemm_f32(int transA, int transB, int M, int N, int K, float al
             cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, ST);
         }
     }
-    gemm_general_kernel<<<grid, 256, 0, ST>>>(g);
+    if (big) gemm_general_kernel<128><<<grid, 256, 0, ST>>>(g);
+    else gemm_general_kernel<64><<<grid, 256, 0, ST>>>(g);
     AM_LAUNCH_CHECK("gemm_f32");
     return AM_OK;
 }

@@ -304,4 +304,5 @@ def test_training_gradients_run_to_run_reproducibility():
     assert torch.allclose(l0, l1, rtol=1e-6, atol=0)  # BatchNorm batch sums are fp64 atomics: order-dependent only far below fp32
     gscale = max(float(v.norm()) for v in g0.values())
     worst = max((((g0[n] - g1[n]).double().norm() / (g0[n].double().norm() + 1e-6 * gscale)).item(), n) for n in g0)
+    print(f"run-to-run gradient difference (relative L2, worst parameter): {worst[0]:.3e} at {worst[1]}")
     assert worst[0] < 5e-3, worst  # measured ~1e-4..1e-3 on the smallest encoder gradients; the oracle gate is 2e-2
