@@ -15,16 +15,13 @@ __device__ __forceinline__ float sqdist_rn(float ax, float ay, float az, float b
     return s;
 }
 
-__device__ __forceinline__ void argmax_merge(float& v, int& i, float ov, int oi) {
-    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
-}
-
 // ---------------------------------------------------------------- farthest point sampling
 // One CTA (1024 threads) per batch segment; the segment's coordinates and running min-distances stay in registers (PPT points per
 // thread) for all m-1 dependent rounds.  Round 2: the m-1 rounds are a latency chain, and each one paid two block barriers plus a
 // GLOBAL read of the winner's coordinates (~1 us per round, 2.15 ms for 8192 -> 2048).  Now the coordinates are also staged in
-// shared memory (<= 8192 points: 96 KB), every warp redundantly reduces the 32 per-warp candidates (double-buffered by round parity),
-// so a round is ONE barrier and no global access on the critical path.  Same arithmetic and tie rule: bit-exact vs the oracle.
+// shared memory (<= 8192 points: 96 KB), every warp redundantly reduces the 32 per-warp candidates (double-buffered by round parity)
+// with redux.sync on the distance bit patterns (the round is issue-bound: 32 warps x ~180 instructions before, ~110 now), so a round
+// is ONE barrier and no global access on the critical path.  Same arithmetic and tie rule: bit-exact vs the oracle.
 constexpr int FPS_THREADS = 1024;
 
 template <int PPT>
@@ -38,7 +35,7 @@ fps_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ offset, co
     const int n = end_n - start_n, m = end_m - start_m;
     if (m <= 0 || n <= 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    __shared__ float s_val[2][32];
+    __shared__ unsigned s_key[2][32];
     __shared__ int s_idx[2][32];
 
     float px[PPT > 0 ? PPT : 1], py[PPT > 0 ? PPT : 1], pz[PPT > 0 ? PPT : 1], pt[PPT > 0 ? PPT : 1];
@@ -85,24 +82,19 @@ fps_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ offset, co
                 if (t > best) { best = t; besti = k; }
             }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            float ov = __shfl_xor_sync(0xffffffffu, best, o);
-            int oi = __shfl_xor_sync(0xffffffffu, besti, o);
-            argmax_merge(best, besti, ov, oi);
-        }
+        // arg-max with ties to the lowest index as two redux.sync per level: distances are >= 0, so their bit patterns order like
+        // unsigned integers; key = bits + 1 keeps 0 for "no candidate" (a thread past the end of the segment)
+        unsigned key = besti == 0x7fffffff ? 0u : __float_as_uint(best) + 1u;
+        unsigned kmax = __reduce_max_sync(0xffffffffu, key);
+        int imin = __reduce_min_sync(0xffffffffu, key == kmax ? besti : 0x7fffffff);
         const int par = j & 1;
-        if (lane == 0) { s_val[par][warp] = best; s_idx[par][warp] = besti; }
+        if (lane == 0) { s_key[par][warp] = kmax; s_idx[par][warp] = imin; }
         __syncthreads();  // the only barrier of the round: the buffer of parity `par` is rewritten two rounds later, after the next barrier
-        best = s_val[par][lane]; besti = s_idx[par][lane];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            float ov = __shfl_xor_sync(0xffffffffu, best, o);
-            int oi = __shfl_xor_sync(0xffffffffu, besti, o);
-            argmax_merge(best, besti, ov, oi);
-        }
-        last = besti;
-        if (tid == 0) idx[start_m + j] = start_n + besti;
+        key = s_key[par][lane];
+        besti = s_idx[par][lane];
+        kmax = __reduce_max_sync(0xffffffffu, key);
+        last = __reduce_min_sync(0xffffffffu, key == kmax ? besti : 0x7fffffff);
+        if (tid == 0) idx[start_m + j] = start_n + last;
     }
 }
 
