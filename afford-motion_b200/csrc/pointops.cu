@@ -15,16 +15,6 @@ __device__ __forceinline__ float sqdist_rn(float ax, float ay, float az, float b
     return s;
 }
 
-// Two squared distances at once with the packed fp32 instructions of sm_100 (add / mul .f32x2, round-to-nearest, no contraction):
-// the same operations in the same order as sqdist_rn, so each half is bit-identical to it.
-__device__ __forceinline__ float2 sqdist2_rn(float2 ax, float2 ay, float2 az, float bx, float by, float bz) {
-    const float2 dx = __fadd2_rn(ax, make_float2(-bx, -bx)), dy = __fadd2_rn(ay, make_float2(-by, -by)), dz = __fadd2_rn(az, make_float2(-bz, -bz));
-    float2 s = __fmul2_rn(dx, dx);
-    s = __fadd2_rn(s, __fmul2_rn(dy, dy));
-    s = __fadd2_rn(s, __fmul2_rn(dz, dz));
-    return s;
-}
-
 // ---------------------------------------------------------------- farthest point sampling
 // One CTA (1024 threads) per batch segment; the segment's coordinates and running min-distances stay in registers (PPT points per
 // thread) for all m-1 dependent rounds.  Round 2: the m-1 rounds are a latency chain, and each one paid two block barriers plus a
@@ -72,15 +62,7 @@ fps_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ offset, co
         else { const float* p = xyz + 3 * (int64_t)(start_n + last); lx = p[0]; ly = p[1]; lz = p[2]; }
         float best = -1.0f;
         int besti = 0x7fffffff;
-        if (PPT >= 2) {
-#pragma unroll
-            for (int i = 0; i < PPT; i += 2) {
-                const float2 d2 = sqdist2_rn(make_float2(px[i], px[i + 1]), make_float2(py[i], py[i + 1]), make_float2(pz[i], pz[i + 1]), lx, ly, lz);
-                const int k0 = tid + i * FPS_THREADS, k1 = k0 + FPS_THREADS;
-                if (k0 < n) { const float t = fminf(pt[i], d2.x); pt[i] = t; if (t > best) { best = t; besti = k0; } }
-                if (k1 < n) { const float t = fminf(pt[i + 1], d2.y); pt[i + 1] = t; if (t > best) { best = t; besti = k1; } }
-            }
-        } else if (PPT > 0) {
+        if (PPT > 0) {
 #pragma unroll
             for (int i = 0; i < PPT; ++i) {
                 int k = tid + i * FPS_THREADS;
@@ -131,7 +113,7 @@ knn_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz, con
     const int q = start_m + blockIdx.x * KNN_THREADS + threadIdx.x;
     if (start_m + blockIdx.x * KNN_THREADS >= end_m) return;  // whole CTA out of range
     const bool active = q < end_m;
-    __shared__ __align__(16) float tx[KNN_TILE], ty[KNN_TILE], tz[KNN_TILE];  // candidate coordinates, structure of arrays
+    __shared__ float4 tile[KNN_TILE];
     float qx = 0.f, qy = 0.f, qz = 0.f;
     if (active) { const float* p = new_xyz + 3 * (int64_t)q; qx = p[0]; qy = p[1]; qz = p[2]; }
     float bd[K];
@@ -145,9 +127,9 @@ knn_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz, con
         for (int i = threadIdx.x; i < cnt4; i += KNN_THREADS) {
             if (i < cnt) {
                 const float* p = xyz + 3 * (int64_t)(t0 + i);
-                tx[i] = p[0]; ty[i] = p[1]; tz[i] = p[2];
+                tile[i] = make_float4(p[0], p[1], p[2], 0.f);
             } else {
-                tx[i] = ty[i] = tz[i] = CUDART_INF_F;  // sentinel: distance +inf, never inserted
+                tile[i] = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, 0.f);  // sentinel: distance +inf, never inserted
             }
         }
         __syncthreads();
@@ -156,12 +138,11 @@ knn_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz, con
             // branch pairs (after the first few hundred candidates almost every group is rejected); an accepted group replays its
             // members in index order with the same strict test, so results are identical to the one-at-a-time loop
             for (int i = 0; i < cnt4; i += 4) {
-                const float4 X = *reinterpret_cast<const float4*>(tx + i), Y = *reinterpret_cast<const float4*>(ty + i),
-                             Z = *reinterpret_cast<const float4*>(tz + i);
-                const float2 d01 = sqdist2_rn(make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(Z.x, Z.y), qx, qy, qz);
-                const float2 d23 = sqdist2_rn(make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(Z.z, Z.w), qx, qy, qz);
-                if (fminf(fminf(d01.x, d01.y), fminf(d23.x, d23.y)) < bd[K - 1]) {
-                    const float dd[4] = {d01.x, d01.y, d23.x, d23.y};
+                const float4 c0 = tile[i], c1 = tile[i + 1], c2 = tile[i + 2], c3 = tile[i + 3];
+                const float d0 = sqdist_rn(c0.x, c0.y, c0.z, qx, qy, qz), d1 = sqdist_rn(c1.x, c1.y, c1.z, qx, qy, qz);
+                const float d2 = sqdist_rn(c2.x, c2.y, c2.z, qx, qy, qz), d3 = sqdist_rn(c3.x, c3.y, c3.z, qx, qy, qz);
+                if (fminf(fminf(d0, d1), fminf(d2, d3)) < bd[K - 1]) {
+                    const float dd[4] = {d0, d1, d2, d3};
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const float d = dd[u];
