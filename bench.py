@@ -252,9 +252,34 @@ def cpu_config4(nsteps, warmup, threads, batch=4):
                       "the reference's CMDM in train mode on the host CPU"}
 
 
+def cpu_full_job(nd, threads):
+    """the WHOLE headline job once on the CPU with the reference's own modules — `diffusion.p_sample_loop(model,
+    (32, 196, 263), clip_denoised=False, model_kwargs=...)` (test.py:94-101), conditioning recomputed on every step."""
+    from amb200 import synth
+    from amb200.config import cmdm_model_cfg
+    inp = synth_host_inputs(0)
+    ref = _ref_setup(cmdm_model_cfg(NPTS), nd, "", B, inp["text"])
+    assert ref is not None, "oracle/_ref is not staged (python oracle/build_ref.py)"
+    model, diff = ref
+    model.eval()
+    kw = dict(c_text=inp["texts"], c_pc_xyz=inp["xyz"], c_pc_contact=inp["contact"], x_mask=inp["x_mask"])
+    torch.manual_seed(2023)
+    t0 = time.perf_counter()
+    out = diff.p_sample_loop(model, (B, T, DM), clip_denoised=False, noise=None, model_kwargs=kw, progress=False)
+    dt = time.perf_counter() - t0
+    return {"workload": bench_config(1, nd)["workload"], "seconds": dt, "denoise_steps_per_s": nd / dt, "motions_per_s": B / dt, "threads": threads,
+            "host_cpus": os.cpu_count(), "finite": bool(torch.isfinite(out).all()), "kind": "reference"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return
+    if args.full_run:
+        threads = args.threads or best_cpu_threads()
+        torch.set_num_threads(threads)
+        os.environ["OMP_NUM_THREADS"] = str(min(threads, B))
+        print(json.dumps(cpu_full_job(args.denoise_steps, threads)))
         return
     threads = best_cpu_threads()
     torch.set_num_threads(threads)
@@ -304,6 +329,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the config3/4/5 and fast-mode legs")
     ap.add_argument("--profile-steps", type=int, default=3)
+    ap.add_argument("--full-run", action="store_true", help="--impl reference only: the whole --denoise-steps job once on the CPU")
+    ap.add_argument("--threads", type=int, default=0, help="--impl reference --full-run: CPU threads (default: fastest on this host)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
