@@ -481,6 +481,8 @@ __global__ void masked_mse_bwd_kernel(const float* __restrict__ x0, const float*
 int am_rowgemm_fwd_(const float* X, int ldx, const float* W, int ldw, int transW, float* Y, int ldy, int M, int N, int K, const float* bias,
                     int act, const float* residual, int ldr, cudaStream_t st);
 int am_rowgemm_dw_(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int R, int P, int Q, cudaStream_t st);
+int am_bgemm_tc_(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb, float beta, float* C,
+                 int ldc, int batch, int bdiv, int64_t sA1, int64_t sA2, int64_t sB1, int64_t sB2, int64_t sC1, int64_t sC2, cudaStream_t st);
 extern "C" int am_gemm_f32(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb, float beta,
                            float* C, int ldc, int batch, int bdiv, int64_t sA1, int64_t sA2, int64_t sB1, int64_t sB2, int64_t sC1, int64_t sC2,
                            am_stream_t stream) {
@@ -494,6 +496,11 @@ extern "C" int am_gemm_f32(int transA, int transB, int M, int N, int K, float al
             if (!transA && am_rowgemm_fwd_(A, lda, B, ldb, 1, C, ldc, M, N, K, nullptr, 0, nullptr, 0, ST)) { AM_LAUNCH_CHECK("gemm_f32"); return AM_OK; }
             if (transA && am_rowgemm_dw_(A, lda, B, ldb, C, ldc, K, M, N, ST)) { AM_LAUNCH_CHECK("gemm_f32"); return AM_OK; }
         }
+    }
+    // batched attention products of the training step: tcgen05 with on-the-fly bf16 (hi|lo) conversion (csrc/bgemm_tc.cu)
+    if (am_bgemm_tc_(transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, batch, bdiv, sA1, sA2, sB1, sB2, sC1, sC2, ST)) {
+        AM_LAUNCH_CHECK("gemm_f32");
+        return AM_OK;
     }
     GemmG g{A, B, C, M, N, K, lda, ldb, ldc, transA, transB, alpha, beta, bdiv, sA1, sA2, sB1, sB2, sC1, sC2, 1, K};
     // 128-row tiles (8 x 4 accumulators per thread) when that still leaves >= 2 waves of CTAs, else 64-row tiles
