@@ -231,7 +231,11 @@ int am_bgemm_tc_(int transA, int transB, int M, int N, int K, float alpha, const
                  int ldc, int batch, int bdiv, int64_t sA1, int64_t sA2, int64_t sB1, int64_t sB2, int64_t sC1, int64_t sC2, cudaStream_t st) {
     static int on = -1;
     if (on < 0) { const char* e = getenv("AMB200_BGEMM"); on = (e && !strcmp(e, "simt")) ? 0 : 1; }
-    if (!on || batch < 8 || M < 32 || N < 32 || K < 16) return 0;
+    // batched attention products, and the un-batched tall GEMMs with odd / short K (TransitionDown linears, K = 35 / 67 / 131: they miss
+    // am_linear_tc's K % 4 rule); deep-K weight gradients stay on the split-K SIMT path
+    const bool batched = batch >= 8 && M >= 32;
+    const bool tall = batch == 1 && M >= 4096 && K <= 512;
+    if (!on || !(batched || tall) || N < 32 || K < 16) return 0;
     BGemm g;
     g.A = A; g.B = B; g.C = C; g.M = M; g.N = N; g.K = K;
     // am_gemm_f32 convention: A is [M,K] (lda) or, transA, [K,M]; B is [K,N] (ldb) or, transB, [N,K]
