@@ -17,6 +17,7 @@
 #include <cuda_bf16.h>
 #include <math_constants.h>
 #include <type_traits>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -31,7 +32,8 @@ constexpr int S_COL = 0, O_COL = 384;
 // smem: Q_hi, Q_lo, K_hi[3], K_lo[3], V_hi[3], V_lo[3]  = 14 tiles = 224 KB
 constexpr int OFF_QH = 0, OFF_QL = TILE_BYTES, OFF_KH = 2 * TILE_BYTES, OFF_KL = 5 * TILE_BYTES, OFF_VH = 8 * TILE_BYTES,
               OFF_VL = 11 * TILE_BYTES, OFF_BAR = 14 * TILE_BYTES;
-constexpr int ATT_SMEM = OFF_BAR + 256 + 1024 + 1024;  // barriers + mask bits, row max/sum exchange [2][128] fp32, alignment slack
+constexpr int ATT_SMEM = OFF_BAR + 256 + 2048 + 768;  // barriers + mask bits, row max and row sum exchange [2][128] fp32 each, alignment slack
+static_assert(ATT_SMEM <= 227 * 1024, "attention shared memory exceeds the 227 KB opt-in limit");
 
 struct AttParams {
     int B, S, H;
@@ -408,6 +410,447 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap tm, AttParams p) {
     if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Round 2: the same arithmetic, software-pipelined across query tiles.  The round-1 kernel above ran each query
+// tile as a strict chain  QK -> row max -> exp/split -> PV -> epilogue  (11.8K cycles per tile of which the tensor pipe was busy
+// 4.6K: `tools/probes/mma_rate_probe.cu` measures M128 N128 K16 at 64 cycles and the N128 + N64 TMEM-A pair of one PV k-step at 96,
+// i.e. at the tcgen05 floor, so the MMAs themselves were never the problem).  Here
+//   * the MMA thread issues QK(t+1, key tile kt) right behind PV(t, last block of key tile kt): tcgen05.mma executes in issue
+//     order, so the P columns of tile t are consumed before S of tile t+1 overwrites them — no second S buffer is needed;
+//   * the softmax warps compute the row max of tile t+1 BEFORE they wait for O of tile t, which hides the PV tail and the QK of
+//     the next tile; the (max, sum) exchanges use separate arrays -> two named barriers per tile instead of four;
+//   * tcgen05.ld is issued one 32-column chunk ahead of the exp / split arithmetic; for that P(hi | lo) of a 32-key chunk is
+//     written back into the chunk's OWN 32 columns (hi words [0,16), lo words [16,32)), so a store never lands in columns a
+//     pending load still needs;
+//   * K tiles arrive on their own barriers (QK of the first tile starts after 1/6 of the K/V bytes instead of all of them).
+__device__ __forceinline__ bool mbar_test_a(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32a(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+// Whole-warp (convergent) variants: every lane of the issuing warp runs the loop and `elect.sync` predicates the instruction
+// itself.  Under a divergent `if (lane == 0)` ptxas lowers each tcgen05.mma to an ELECT / R2UR / BRA.U.ANY loop over the active lanes.
+__device__ __forceinline__ void umma_ss_w(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_ts_w(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit_w(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32a(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t r[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+// wait for every outstanding tcgen05.ld of this thread; the registers are operands so that no use of them is scheduled above the wait
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t r[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+          "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+          "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
+          "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+        :: "memory");
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+mha_tc_pipe_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tmo, AttParams p) {
+    pdl_launch_dependents();
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint64_t* k_full = bars + 0;    // [3] one per 128-key K tile
+    uint64_t* v_full = bars + 3;
+    uint64_t* q_full = bars + 4;
+    uint64_t* q_empty = bars + 5;
+    uint64_t* o_full = bars + 6;
+    uint64_t* o_free = bars + 7;    // 256 arrivals: both softmax groups have read O of the tile
+    uint64_t* s_full = bars + 8;    // [3] one per 128-key tile of S
+    uint64_t* p_ready = bars + 11;  // [12] one per 32-key chunk of P
+    uint64_t* stage_full = bars + 23;   // 256 arrivals: O of the tile is staged (bf16 hi | lo) in the Q buffer
+    uint64_t* q_free = bars + 24;       // the TMA store has read the staged tile: Q of the tile after next may be loaded
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 25);
+    uint32_t* maskbits = tmem_holder + 1;  // [12] bit k of word w: key 32w+k is attendable
+    float* xmax = reinterpret_cast<float*>(smem + OFF_BAR + 256);   // [2][128]
+    float* xsum = xmax + 256;                                         // [2][128]
+    if (smem - smem_raw > 768) __trap();   // the 1024-byte round-up above may use at most the 768 bytes of slack in ATT_SMEM
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+    const int S = p.S, D = p.H * HD;
+    const int nq = (S + QT - 1) / QT;
+    const int nblk = (S + 63) / 64;
+    const int nkt = (S + KT - 1) / KT;
+
+    if (warp == 10 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmo)) : "memory");
+    }
+    if (warp == 11 && lane == 0) {
+        for (int j = 0; j < 3; ++j) { mbar_init_a(&k_full[j], 1); mbar_init_a(&s_full[j], 1); }
+        mbar_init_a(v_full, 1); mbar_init_a(q_full, 1); mbar_init_a(q_empty, 1); mbar_init_a(o_full, 1);
+        mbar_init_a(o_free, 256);
+        mbar_init_a(stage_full, 256); mbar_init_a(q_free, 1);
+        for (int j = 0; j < 12; ++j) mbar_init_a(&p_ready[j], 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32a(tmem_holder)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp == 9 && lane < 12) {
+        pdl_wait();
+        uint32_t bits = 0;
+        for (int k = 0; k < 32; ++k) {
+            int key = lane * 32 + k;
+            bool ok = key < S && !(p.key_pad && p.key_pad[(int64_t)b * S + key]);
+            bits |= ok ? (1u << k) : 0u;
+        }
+        maskbits[lane] = bits;
+    }
+    fence_before_a();
+    __syncthreads();
+    fence_after_a();
+    // All 512 columns are allocated (one CTA per SM), so the allocation can only start at column 0.  Treating the base as the
+    // CONSTANT 0 keeps every TMEM operand of the single-thread MMA loop in uniform registers; with a base loaded from shared memory
+    // ptxas wraps each tcgen05.mma in an ELECT / R2UR / branch loop, and the issuing thread (not the tensor pipe) paces the kernel
+    // (measured: 96 cycles per MMA issued against a 32-64 cycle floor).
+    if (*tmem_holder != 0u) __trap();
+    constexpr uint32_t tmem_base = 0u;
+    pdl_wait();
+    const bool dbg = p.dbg && blockIdx.x == 0;
+    if (dbg && threadIdx.x == 320) p.dbg[0] = clock64();
+
+    if (warp == 10) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            auto produce = [&](auto fc) {
+                constexpr bool FAST = decltype(fc)::value;
+                mbar_expect_tx_a(q_full, (FAST ? 1 : 2) * TILE_BYTES);
+                tma_load_3d(smem + OFF_QH, &tm, q_full, h * HD, 0, b);
+                if (!FAST) tma_load_3d(smem + OFF_QL, &tm, q_full, 3 * D + h * HD, 0, b);
+                for (int kt = 0; kt < NKT; ++kt) {
+                    mbar_expect_tx_a(&k_full[kt], (FAST ? 1 : 2) * TILE_BYTES);
+                    tma_load_3d(smem + OFF_KH + kt * TILE_BYTES, &tm, &k_full[kt], D + h * HD, kt * KT, b);
+                    if (!FAST) tma_load_3d(smem + OFF_KL + kt * TILE_BYTES, &tm, &k_full[kt], 3 * D + D + h * HD, kt * KT, b);
+                }
+                mbar_expect_tx_a(v_full, (FAST ? 3 : 6) * TILE_BYTES);
+                for (int kt = 0; kt < NKT; ++kt) {
+                    tma_load_3d(smem + OFF_VH + kt * TILE_BYTES, &tm, v_full, 2 * D + h * HD, kt * KT, b);
+                    if (!FAST) tma_load_3d(smem + OFF_VL + kt * TILE_BYTES, &tm, v_full, 3 * D + 2 * D + h * HD, kt * KT, b);
+                }
+                for (int t = 1; t < nq; ++t) {
+                    // the Q buffer doubles as the staging tile of the epilogue: Q(1) may land once S of tile 0 is complete; Q(t >= 2)
+                    // once the TMA store of tile t-2 has read its staged O (the epilogue staged it after S of tile t-1 was complete)
+                    if (t == 1) mbar_wait_a(q_empty, 0); else mbar_wait_a(q_free, (t - 2) & 1);
+                    mbar_expect_tx_a(q_full, (FAST ? 1 : 2) * TILE_BYTES);
+                    tma_load_3d(smem + OFF_QH, &tm, q_full, h * HD, t * QT, b);
+                    if (!FAST) tma_load_3d(smem + OFF_QL, &tm, q_full, 3 * D + h * HD, t * QT, b);
+                }
+            };
+            if (p.fast) produce(std::true_type{}); else produce(std::false_type{});
+        }
+    } else if (warp == 11) {
+        // ===================== MMA issuer (whole warp, elect.sync per instruction) =====================
+        {
+            auto issue = [&](auto fc) {
+                constexpr bool FAST = decltype(fc)::value;
+                const uint32_t sb = smem_u32a(smem);
+                const uint64_t qh = desc_kmajor(sb + OFF_QH), ql = desc_kmajor(sb + OFF_QL);
+                // keys of the last key tile rounded up to the MMA's N granularity (16): S = 326 -> 80 columns instead of 128.  The
+                // columns beyond are never written; the key mask keeps the softmax away from them.
+                const int n_last = min(KT, ((S - (nkt - 1) * KT + 15) >> 4) << 4);
+                // S(t)[:, 128 kt0 : 128 kt0 + ncols] = Q K^T, 3-term split.  Consecutive K tiles are contiguous in shared memory
+                // (8-row groups 1024 B apart throughout), so key tiles 0 and 1 are ONE N = 256 operand.
+                auto qk = [&](int kt0, int ncols) {
+                    const uint64_t kh = desc_kmajor(sb + OFF_KH + kt0 * TILE_BYTES), kl = desc_kmajor(sb + OFF_KL + kt0 * TILE_BYTES);
+                    const uint32_t d = tmem_base + S_COL + kt0 * KT;
+                    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ncols >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+#pragma unroll
+                    for (int k = 0; k < HD / 16; ++k) {
+                        const uint64_t ko = (uint64_t)(k * 2);
+                        if (FAST) { umma_ss_w(d, qh + ko, kh + ko, idesc, k ? 1u : 0u); continue; }
+                        umma_ss_w(d, ql + ko, kh + ko, idesc, k ? 1u : 0u);
+                        umma_ss_w(d, qh + ko, kl + ko, idesc, 1u);
+                        umma_ss_w(d, qh + ko, kh + ko, idesc, 1u);
+                    }
+                };
+                // prologue: S of tile 0, each key tile as soon as its K tile has landed
+                mbar_wait_a(q_full, 0);
+                if (dbg && lane == 0) p.dbg[8] = clock64();
+                for (int kt = 0; kt < nkt; ++kt) {
+                    mbar_wait_a(&k_full[kt], 0);
+                    if (dbg && lane == 0 && kt == 0) p.dbg[1] = clock64();
+                    fence_after_a();
+                    qk(kt, kt == nkt - 1 ? n_last : KT);
+                    umma_commit_w(&s_full[kt]);
+                }
+                umma_commit_w(q_empty);
+                if (dbg && lane == 0) p.dbg[16] = clock64();
+                mbar_wait_a(v_full, 0);
+                for (int t = 0; t < nq; ++t) {
+                    const uint32_t pt = t & 1;
+                    const bool more = t + 1 < nq;
+                    for (int kt = 0; kt < nkt; ++kt) {
+                        // the two softmax groups work on blocks 2 kt and 2 kt + 1 side by side: consume their 32-key chunks alternately
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const int j = 2 * kt + (c & 1), hlf = c >> 1;
+                            if (j >= nblk) continue;
+                            mbar_wait_a(&p_ready[2 * j + hlf], pt);
+                            if (kt == 0 && c == 0 && t > 0) mbar_wait_a(o_free, (t - 1) & 1);   // the epilogue of tile t-1 has read O
+                            fence_after_a();
+                            if (dbg && lane == 0 && t == 1) p.dbg[64 + 2 * j + hlf] = clock64();
+                            const uint32_t voff = (uint32_t)(j * 64) * 128u;
+#pragma unroll
+                            for (int kk = 0; kk < 2; ++kk) {
+                                // 16 keys per MMA; P_hi words of chunk (j, hlf) at column 64 j + 32 hlf + 8 kk, P_lo 16 columns further
+                                const int k = 2 * hlf + kk;
+                                const uint32_t a_hi = tmem_base + S_COL + j * 64 + hlf * 32 + kk * 8, a_lo = a_hi + 16;
+                                const uint64_t vhl = desc_mnmajor_hilo(sb + OFF_VH + voff + k * 2048), vh = desc_mnmajor(sb + OFF_VH + voff + k * 2048);
+                                const uint32_t acc = (kt | c | kk) ? 1u : 0u;
+                                if (FAST) { umma_ts_w(tmem_base + O_COL, a_hi, vh, IDESC_PV, acc); continue; }
+                                umma_ts_w(tmem_base + O_COL, a_hi, vhl, IDESC_PV2, acc);
+                                umma_ts_w(tmem_base + O_COL, a_lo, vh, IDESC_PV, 1u);
+                            }
+                        }
+                        if (dbg && lane == 0 && t == 1) p.dbg[80 + kt] = clock64();
+                        if (kt == nkt - 1) {
+                            umma_commit_w(o_full);
+                            if (dbg && lane == 0) p.dbg[24 + t] = clock64();
+                        }
+                        // the P columns of key tile kt are consumed (tcgen05.mma executes in issue order) -> S of the NEXT query tile
+                        // may overwrite them.  One N = 128 MMA group per key tile (merging tiles 0 and 1 into N = 256 saved 12 MMAs but
+                        // held back P V of key tile 2, which gates the epilogue).
+                        if (more) {
+                            if (kt == 0) {
+                                mbar_wait_a(q_full, (t + 1) & 1);
+                                fence_after_a();
+                                if (dbg && lane == 0) p.dbg[8 + t + 1] = clock64();
+                            }
+                            qk(kt, kt == nkt - 1 ? n_last : KT);
+                            umma_commit_w(&s_full[kt]);
+                            if (dbg && lane == 0 && t == 1) p.dbg[88 + kt] = clock64();
+                            if (dbg && lane == 0 && kt == nkt - 1) p.dbg[16 + t + 1] = clock64();
+                        }
+                    }
+                }
+            };
+            if (p.fast) issue(std::true_type{}); else issue(std::false_type{});
+        }
+    } else if (warp == 9) {
+        // ===================== O store: TMA store of the staged tile =====================
+        if (lane == 0) {
+            for (int t = 0; t < nq; ++t) {
+                mbar_wait_a(stage_full, t & 1);
+                if (p.out2) {
+                    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                                 ::"l"(reinterpret_cast<uint64_t>(&tmo)), "r"(smem_u32a(smem + OFF_QH)), "r"(h * HD), "r"(t * QT), "r"(b) : "memory");
+                    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                                 ::"l"(reinterpret_cast<uint64_t>(&tmo)), "r"(smem_u32a(smem + OFF_QL)), "r"(D + h * HD), "r"(t * QT), "r"(b) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                }
+                mbar_arrive_a(q_free);
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+    } else if (warp < 8) {
+        // ===================== softmax + epilogue =====================
+        const int q4 = warp & 3, grp = warp >> 2;
+        const int r = q4 * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16);
+        const float sc2 = p.scale * 1.4426950408889634f;
+        uint32_t va[32], vb[32];
+
+        // row max of the raw scores of tile t over this group's blocks, tcgen05.ld one chunk ahead of the fmax chain
+        auto chunk_max = [&](const uint32_t (&v)[32], int j, int hlf, float mx) {
+            const uint32_t mb = maskbits[2 * j + hlf];
+            if (mb == 0xffffffffu) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(v[c]));
+            } else {
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                    if ((mb >> c) & 1u) mx = fmaxf(mx, __uint_as_float(v[c]));
+            }
+            return mx;
+        };
+        // blocks [jlo, jhi) of this group (every other block starting at grp)
+        auto pass1 = [&](int t, int jlo, int jhi, float mx) {
+            const uint32_t pt = t & 1;
+            int j = grp;
+            while (j < jlo) j += 2;
+            if (j >= jhi) return mx;
+            mbar_wait_a(&s_full[j >> 1], pt);
+            fence_after_a();
+            if (dbg && threadIdx.x == 0 && jlo == 0) p.dbg[32 + t] = clock64();
+            tmem_ld32_issue(lane_addr + S_COL + j * 64, va);
+            for (; j < jhi; j += 2) {
+                tmem_ld32_wait(va);
+                tmem_ld32_issue(lane_addr + S_COL + j * 64 + 32, vb);
+                mx = chunk_max(va, j, 0, mx);
+                tmem_ld32_wait(vb);
+                const int jn = j + 2;
+                bool pre = false;
+                if (jn < jhi && mbar_test_a(&s_full[jn >> 1], pt)) {   // next block's key tile already complete: prefetch under the fmax chain
+                    fence_after_a();
+                    tmem_ld32_issue(lane_addr + S_COL + jn * 64, va);
+                    pre = true;
+                }
+                mx = chunk_max(vb, j, 1, mx);
+                if (jn < jhi && !pre) {
+                    mbar_wait_a(&s_full[jn >> 1], pt);
+                    fence_after_a();
+                    tmem_ld32_issue(lane_addr + S_COL + jn * 64, va);
+                }
+            }
+            return mx;
+        };
+        // p = 2^(s*sc2 - mx2) of one 32-key chunk -> packed bf16 hi words [0,16) | lo words [16,32) of the chunk's own columns
+        auto chunk_exp = [&](const uint32_t (&v)[32], int j, int hlf, float mx2, float& sum) {
+            const uint32_t mb = maskbits[2 * j + hlf];
+            uint32_t ph[16], pl[16];
+            if (mb == 0xffffffffu) {
+#pragma unroll
+                for (int c = 0; c < 32; c += 2) {
+                    const float e0 = ex2_approx(fmaf(__uint_as_float(v[c]), sc2, -mx2));
+                    const float e1 = ex2_approx(fmaf(__uint_as_float(v[c + 1]), sc2, -mx2));
+                    sum += e0 + e1;
+                    split_pair(e0, e1, ph[c / 2], pl[c / 2]);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 32; c += 2) {
+                    const float e0 = ((mb >> c) & 1u) ? ex2_approx(fmaf(__uint_as_float(v[c]), sc2, -mx2)) : 0.f;
+                    const float e1 = ((mb >> (c + 1)) & 1u) ? ex2_approx(fmaf(__uint_as_float(v[c + 1]), sc2, -mx2)) : 0.f;
+                    sum += e0 + e1;
+                    split_pair(e0, e1, ph[c / 2], pl[c / 2]);
+                }
+            }
+            tmem_st16a(lane_addr + S_COL + j * 64 + hlf * 32, ph);
+            tmem_st16a(lane_addr + S_COL + j * 64 + hlf * 32 + 16, pl);
+            tmem_wait_st();
+            fence_before_a();
+            mbar_arrive_a(&p_ready[2 * j + hlf]);
+        };
+
+        float mx_own = pass1(0, 0, nblk, -CUDART_INF_F);
+        const int jsplit = min(nblk, 4);   // blocks of key tiles 0, 1 | key tile 2
+        for (int t = 0; t < nq; ++t) {
+            const uint32_t pt = t & 1;
+            const int qi = t * QT + r;
+            xmax[grp * 128 + r] = mx_own;
+            softmax_bar();
+            const float mx2 = fmaxf(mx_own, xmax[(grp ^ 1) * 128 + r]) * sc2;
+            if (dbg && threadIdx.x == 0) p.dbg[40 + t] = clock64();
+            // pass 2
+            float sum = 0.f;
+            if (grp < nblk) tmem_ld32_issue(lane_addr + S_COL + grp * 64, va);
+            for (int j = grp; j < nblk; j += 2) {
+                tmem_ld32_wait(va);
+                tmem_ld32_issue(lane_addr + S_COL + j * 64 + 32, vb);
+                chunk_exp(va, j, 0, mx2, sum);
+                tmem_ld32_wait(vb);
+                if (j + 2 < nblk) tmem_ld32_issue(lane_addr + S_COL + (j + 2) * 64, va);
+                chunk_exp(vb, j, 1, mx2, sum);
+                if (dbg && t == 1 && (threadIdx.x & 127) == 0) p.dbg[96 + j] = clock64();
+            }
+            if (dbg && threadIdx.x == 0) p.dbg[48 + t] = clock64();
+            // row max of the NEXT tile over key tiles 0, 1 (their S is complete: it was issued behind P V of blocks 0-3) while the
+            // tensor pipe finishes P V of this tile and S of key tile 2
+            if (t + 1 < nq) mx_own = pass1(t + 1, 0, jsplit, -CUDART_INF_F);
+            xsum[grp * 128 + r] = sum;
+            softmax_bar();
+            sum += xsum[(grp ^ 1) * 128 + r];
+            // epilogue: this group's 32 output columns of O / rowsum
+            mbar_wait_a(o_full, pt);
+            fence_after_a();
+            if (dbg && threadIdx.x == 0) p.dbg[56 + t] = clock64();
+            if (p.fast) {
+                tmem_ld32_issue(lane_addr + O_COL + grp * 32, va);
+                tmem_ld32_wait(va);
+            } else {
+                tmem_ld32_issue(lane_addr + O_COL + grp * 32, va);
+                tmem_ld32_issue(lane_addr + O_COL + HD + grp * 32, vb);   // the P_hi . V_lo term
+                tmem_ld32_wait(va);
+                tmem_ld32_wait(vb);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) va[c] = __float_as_uint(__uint_as_float(va[c]) + __uint_as_float(vb[c]));
+            }
+            fence_before_a();
+            mbar_arrive_a(o_free);
+            if (dbg && (threadIdx.x & 127) == 0) p.dbg[104 + 4 * t + grp] = clock64();
+            if (qi < S) {
+                const float inv = 1.0f / sum;
+                const int64_t row = (int64_t)b * S + qi;
+                if (p.out) {
+                    float* dst = p.out + row * D + h * HD + grp * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(va[j]) * inv, __uint_as_float(va[j + 1]) * inv,
+                                                                          __uint_as_float(va[j + 2]) * inv, __uint_as_float(va[j + 3]) * inv);
+                }
+            }
+            {
+                // bf16 (hi | lo) of O / rowsum staged in the Q buffer (SWIZZLE_128B rows of 64 bf16: 16-byte chunk c of row r sits at
+                // chunk c ^ (r % 8)) and written by TMA: with one row per lane a direct store touches 32 cache lines per instruction
+                // and the 8 x 16-byte stores per thread cost 2-3.4K cycles per tile (measured); rows >= S are clipped by the tensor map.
+                if (t + 1 < nq) mbar_wait_a(&s_full[nkt - 1], (t + 1) & 1);   // S of the next tile is complete: Q is no longer being read
+                if (t > 0) mbar_wait_a(q_free, (t - 1) & 1);                   // the previous tile's store has read its staging
+                if (p.out2) {
+                    const float inv = 1.0f / sum;
+                    uint32_t wh[16], wl[16];
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) split_pair(__uint_as_float(va[j]) * inv, __uint_as_float(va[j + 1]) * inv, wh[j / 2], wl[j / 2]);
+                    uint8_t* sh = smem + OFF_QH + r * 128;
+                    uint8_t* sl = smem + OFF_QL + r * 128;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int off = ((grp * 4 + c) ^ (r & 7)) << 4;
+                        *reinterpret_cast<uint4*>(sh + off) = make_uint4(wh[4 * c], wh[4 * c + 1], wh[4 * c + 2], wh[4 * c + 3]);
+                        *reinterpret_cast<uint4*>(sl + off) = make_uint4(wl[4 * c], wl[4 * c + 1], wl[4 * c + 2], wl[4 * c + 3]);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                }
+                mbar_arrive_a(stage_full);
+            }
+            if (dbg && (threadIdx.x & 127) == 0) p.dbg[104 + 4 * t + 2 + grp] = clock64();
+            if (t + 1 < nq) mx_own = pass1(t + 1, jsplit, nblk, mx_own);   // key tile 2 of the next tile
+        }
+    }
+    fence_before_a();
+    __syncthreads();
+    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
 typedef CUresult (*EncodeTiledFnA)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -446,15 +889,31 @@ extern "C" int am_mha_tc_fwd(const void* qkv2, float* out, void* out2, const uin
         return AM_ELAUNCH;
     }
     static bool attr = false;
+    static bool pipe = true;   // AMB200_ATTN_PIPE=0: the round-1 kernel (one strict chain per query tile), kept for A/B timing
     if (!attr) {
-        if (cudaFuncSetAttribute(mha_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM) != cudaSuccess) {
+        const char* e = getenv("AMB200_ATTN_PIPE");
+        pipe = !(e && e[0] == '0');
+        if (cudaFuncSetAttribute(mha_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM) != cudaSuccess ||
+            cudaFuncSetAttribute(mha_tc_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM) != cudaSuccess) {
             am_set_error_("am_mha_tc_fwd: shared memory opt-in failed");
             return AM_ELAUNCH;
         }
         attr = true;
     }
     AttParams p{B, S, H, scale, key_pad, out, reinterpret_cast<__nv_bfloat16*>(out2), g_att_dbg, am_get_precision()};
-    am_launch(mha_tc_kernel, dim3(B * H), dim3(ATT_THREADS), ATT_SMEM, as_stream(stream), 1, tm, p);
+    CUtensorMap tmo = tm;   // store map of the bf16 (hi | lo) output [B, S, 2 H 64]: 128-row x 64-column boxes, rows >= S clipped
+    if (pipe && out2) {
+        const uint64_t ocols = (uint64_t)2 * H * HD;
+        cuuint64_t odim[3] = {ocols, (cuuint64_t)S, (cuuint64_t)B};
+        cuuint64_t ostr[2] = {ocols * 2, ocols * 2 * (cuuint64_t)S};
+        if (enc(&tmo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, out2, odim, ostr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+            am_set_error_("am_mha_tc_fwd: cuTensorMapEncodeTiled (output) failed");
+            return AM_ELAUNCH;
+        }
+    }
+    if (pipe) am_launch(mha_tc_pipe_kernel, dim3(B * H), dim3(ATT_THREADS), ATT_SMEM, as_stream(stream), 1, tm, tmo, p);
+    else am_launch(mha_tc_kernel, dim3(B * H), dim3(ATT_THREADS), ATT_SMEM, as_stream(stream), 1, tm, p);
     AM_LAUNCH_CHECK("mha_tc_fwd");
     return AM_OK;
 }

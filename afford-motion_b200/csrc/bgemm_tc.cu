@@ -46,9 +46,10 @@ __device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void umma_b(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
+        "{\n\t.reg .pred p, q;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        "elect.sync _|q, 0xffffffff;\n\t"   // issued by one lane of a CONVERGENT warp (a divergent `tid == 0` makes ptxas loop over lanes)
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16_b(uint32_t taddr, uint32_t r[16]) {
@@ -165,7 +166,7 @@ bgemm_tc_kernel(BGemm g) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> tensor-core reads
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint64_t dah = desc_b(a_hi, g.a_mn ? 8192u : 0u), dal = desc_b(a_lo, g.a_mn ? 8192u : 0u);
             const uint64_t dbh = desc_b(b_hi, g.b_mn ? 8192u : 0u), dbl = desc_b(b_lo, g.b_mn ? 8192u : 0u);
@@ -176,7 +177,8 @@ bgemm_tc_kernel(BGemm g) {
                 umma_b(tmem_base, dah + k * ka, dbl + k * kbs, idesc, 1u);
                 umma_b(tmem_base, dah + k * ka, dbh + k * kbs, idesc, 1u);
             }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32b(bar)) : "memory");
+            asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+                         ::"r"(smem_u32b(bar)) : "memory");
         }
         mbar_wait_b(bar, phase);   // the MMAs have finished reading this K block's tiles (and, on the last block, writing the accumulator)
         phase ^= 1u;

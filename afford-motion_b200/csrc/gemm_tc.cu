@@ -1153,8 +1153,10 @@ gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             if (p.fast) produce(std::true_type{}); else produce(std::false_type{});
         }
     } else if (warp == MMA_WARP) {
-        // ===================== MMA issuer: one thread of the LEADER CTA for the pair =====================
-        if (lane == 0 && leader) {
+        // ===================== MMA issuer: the LEADER CTA's warp for the pair =====================
+        // The whole warp runs the loop (convergent) and `elect.sync` predicates each tcgen05 instruction: under a divergent
+        // `if (lane == 0)` ptxas wraps every tcgen05.mma in an ELECT / 7 x R2UR.BROADCAST / BRA.U.ANY loop over the active lanes.
+        if (leader) {
             auto issue = [&](auto fc) {
             constexpr bool FAST = decltype(fc)::value;
             uint32_t kbc = 0;
@@ -1176,7 +1178,7 @@ gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     for (int k = 0; k < BK / 16; ++k) {
                         const uint64_t ko = (uint64_t)(k * 2);
 #define AM_UMMA_2SM(a_, b_, acc_)                                                                                     \
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" \
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" \
                  ::"r"(d), "l"(a_), "l"(b_), "r"(idesc), "r"((uint32_t)(acc_)) : "memory")
                         if (FAST) { AM_UMMA_2SM(a_hi + ko, w_hi + ko, (kb | k) ? 1u : 0u); continue; }
                         AM_UMMA_2SM(a_lo + ko, w_hi + ko, (kb | k) ? 1u : 0u);
@@ -1184,12 +1186,12 @@ gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         AM_UMMA_2SM(a_hi + ko, w_hi + ko, 1u);
 #undef AM_UMMA_2SM
                     }
-                    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
                                  ::"r"(smem_u32(&empty[s])), "h"((uint16_t)3) : "memory");
                 }
-                asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
                              ::"r"(smem_u32(&tmem_full[ab])), "h"((uint16_t)3) : "memory");
-                if (dbg && it < 16) p.dbg[8 + it] = clock64();
+                if (dbg && lane == 0 && it < 16) p.dbg[8 + it] = clock64();
             }
             };
             if (p.fast) issue(std::true_type{}); else issue(std::false_type{});

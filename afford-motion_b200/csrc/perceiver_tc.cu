@@ -308,13 +308,15 @@ __device__ __forceinline__ void mbar_wait_p(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void umma_ss_p(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
+        "{\n\t.reg .pred p, q;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        "elect.sync _|q, 0xffffffff;\n\t"   // one lane of a CONVERGENT warp (a divergent `tid == 0` makes ptxas loop over the active lanes)
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
 __device__ __forceinline__ void umma_commit_p(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32p(bar)) : "memory");
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+                 ::"r"(smem_u32p(bar)) : "memory");
 }
 __device__ __forceinline__ void tc_before_p() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_after_p() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -473,7 +475,7 @@ cdm_dec_points_tc_kernel(const float* __restrict__ x_t, const float* __restrict_
         tc_before_p();
         __syncthreads();
         // ---------------- the dense layer: D[128 x 256] = Z[128 x 32] M^T, 3-term split, one elected thread
-        if (tid == 0) {
+        if (tid < 32) {
             tc_after_p();
             const uint64_t dah = make_desc64_p(smem_u32p(smem + SO_AH)), dal = make_desc64_p(smem_u32p(smem + SO_AL));
             const uint64_t dbh = make_desc64_p(smem_u32p(smem + SO_BH)), dbl = make_desc64_p(smem_u32p(smem + SO_BL));

@@ -289,7 +289,7 @@ def test_layernorm_and_attention_vs_torch():
         assert (out.cpu().double() - ref).abs().max() < 2e-5
 
 
-@pytest.mark.parametrize("B,S", [(3, 326), (2, 212), (1, 130), (2, 384), (1, 40)])
+@pytest.mark.parametrize("B,S", [(3, 326), (2, 212), (1, 130), (2, 384), (1, 40), (2, 300), (2, 256), (1, 128), (40, 326)])
 def test_mha_tc_vs_fp64(B, S):
     """tcgen05 attention (P in TMEM, 3-term bf16 split) vs an fp64 softmax(QK^T/8 + mask)V reference."""
     g = torch.Generator().manual_seed(S)
