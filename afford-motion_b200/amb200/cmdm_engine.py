@@ -46,6 +46,8 @@ class CMDMEngine:
         # measured 44.3 / 58.9 us against 34.1 / 42.8 us for GEMM + LayerNorm (profiles/r2_gemm_ln_fused_ab.txt) — its row-per-lane
         # epilogue is bound by uncoalesced residual / output accesses; parity-tested, kept for the next round
         self.fuse_ln = os.environ.get("AMB200_LN_FUSE", "0") == "1"
+        # last encoder layer on the motion rows only (am_mha_tc_fwd_rows); needs the pipelined attention kernel
+        self.last_compact = os.environ.get("AMB200_LAST_COMPACT", "1") == "1" and os.environ.get("AMB200_ATTN_PIPE", "1") != "0"
         assert self.attn in ("tc", "simt")
 
     # ------------------------------------------------------------------ weights
@@ -153,7 +155,8 @@ class CMDMEngine:
             if self.gemm == "tc":
                 bf = lambda r, c: torch.zeros(r, c, dtype=torch.bfloat16, device=dev)
                 ws.update({"X0S": bf(M, 2 * D), "XSa": bf(M, 2 * D), "XSb": bf(M, 2 * D), "ATTS": bf(M, 2 * D), "Y1S": bf(M, 2 * D),
-                           "FFS": bf(M, 2 * ops.pad32(ff)), "xS": bf(B * T, 2 * ops.pad32(self.m.motion_dim)), "QKVS": bf(M, 6 * D)})
+                           "FFS": bf(M, 2 * ops.pad32(ff)), "xS": bf(B * T, 2 * ops.pad32(self.m.motion_dim)), "QKVS": bf(M, 6 * D),
+                           "RS": bf(B * T, 2 * D)})
             self._ws[key] = ws
         return ws
 
@@ -236,16 +239,23 @@ class CMDMEngine:
         cur, curS = X0.view(M, D), X0S
         ffp = ops.pad32(self.ff)
         fuse_ln = self.fuse_ln and D == 512 and ffp % 64 == 0
+        compact = False
         for i in range(self.nlayers):
             p = f"l{i}."
             last = i == self.nlayers - 1
             nxt, nxtS = (ws["Xa"], ws["XSa"]) if i % 2 == 0 else (ws["Xb"], ws["XSb"])
+            # The last layer's output is only read at the motion tokens (models/cmdm.py:183-186 slices x[non_motion_token:]) and
+            # every row is independent after the attention: its attention runs on the query rows [2+G, S) only and writes them
+            # compactly, and out_proj / LayerNorm / feed-forward / motion_layer run on B*T rows instead of B*S (60 % at T=196, G=128).
+            compact = last and self.last_compact and self.attn == "tc" and S <= 384 and hd == 64 and not fuse_ln
+            Mr = B * T if compact else M     # rows from the attention output onwards
+            resS = curS
             if self.attn == "tc" and S <= 384 and hd == 64:
                 ops.linear_tc(curS, w[p + "in_w2"], M, 3 * D, D, y2=ws["QKVS"], bias=w[p + "in_b"], Np2=3 * D)
-                ops.mha_tc_fwd(ws["QKVS"], None, ws["ATTS"], cond.key_pad, B, S, H, hd, 1.0 / math.sqrt(hd))
-            else:
-                ops.linear_tc(curS, w[p + "in_w2"], M, 3 * D, D, y=ws["QKV"], bias=w[p + "in_b"])
-                ops.mha_fwd(ws["QKV"], None, cond.key_pad, B, S, H, hd, 1.0 / math.sqrt(hd), out2=ws["ATTS"])
+                ops.mha_tc_fwd(ws["QKVS"], None, ws["ATTS"], cond.key_pad, B, S, H, hd, 1.0 / math.sqrt(hd), q_row0=2 + G if compact else 0)
+                if compact:   # the residual stream of the same rows
+                    ws["RS"].view(B, T, 2 * D).copy_(curS.view(B, S, 2 * D)[:, 2 + G:, :])
+                    resS = ws["RS"]
             # residual streams travel as the bf16 (hi|lo) pairs the LayerNorm / adapter epilogues already write for the next
             # GEMM's A operand (x = hi + lo, 16 significant bits): no fp32 copy of the activations is written at all
             if fuse_ln:
@@ -255,14 +265,16 @@ class CMDMEngine:
                 ops.linear_tc(ws["Y1S"], w[p + "w12"], M, self.ff, D, y2=ws["FFS"], bias=w[p + "b1"], act="gelu", Np2=ffp)
                 ops.linear_ln_tc(ws["FFS"], w[p + "w22"], M, D, ffp, w[p + "b2"], ws["Y1S"], w[p + "n2g"], w[p + "n2b"], w[p + "eps2"], nxtS)
             else:
-                ops.linear_tc(ws["ATTS"], w[p + "out_w2"], M, D, D, y=ws["TMP"], bias=w[p + "out_b"], residual_split=curS)
-                ops.layernorm(ws["TMP"], w[p + "n1g"], w[p + "n1b"], None, M, D, eps=w[p + "eps1"], y2=ws["Y1S"])
-                ops.linear_tc(ws["Y1S"], w[p + "w12"], M, self.ff, D, y2=ws["FFS"], bias=w[p + "b1"], act="gelu", Np2=ffp)
-                ops.linear_tc(ws["FFS"], w[p + "w22"], M, D, ffp, y=ws["TMP"], bias=w[p + "b2"], residual_split=ws["Y1S"])
-                ops.layernorm(ws["TMP"], w[p + "n2g"], w[p + "n2b"], None, M, D, eps=w[p + "eps2"], y2=nxtS)
+                ops.linear_tc(ws["ATTS"], w[p + "out_w2"], Mr, D, D, y=ws["TMP"], bias=w[p + "out_b"], residual_split=resS)
+                ops.layernorm(ws["TMP"], w[p + "n1g"], w[p + "n1b"], None, Mr, D, eps=w[p + "eps1"], y2=ws["Y1S"])
+                ops.linear_tc(ws["Y1S"], w[p + "w12"], Mr, self.ff, D, y2=ws["FFS"], bias=w[p + "b1"], act="gelu", Np2=ffp)
+                ops.linear_tc(ws["FFS"], w[p + "w22"], Mr, D, ffp, y=ws["TMP"], bias=w[p + "b2"], residual_split=ws["Y1S"])
+                ops.layernorm(ws["TMP"], w[p + "n2g"], w[p + "n2b"], None, Mr, D, eps=w[p + "eps2"], y2=nxtS)
             cur, curS = nxt, nxtS
         if out is None:
             out = torch.empty(B, T, Dm, device=x.device)
-        # motion_layer over all tokens; only rows s >= 2+G are written (skip map) -> out [B*T, Dm]
-        ops.linear_tc(curS, w["motion_layer.w2"], M, Dm, D, y=out, bias=w["motion_layer.b"], ymap=(S, T, -(2 + G)), ldy=Dm)
+        if self.nlayers and compact:   # curS already holds the B*T motion rows
+            ops.linear_tc(curS, w["motion_layer.w2"], B * T, Dm, D, y=out, bias=w["motion_layer.b"], ldy=Dm)
+        else:   # motion_layer over all tokens; only rows s >= 2+G are written (skip map) -> out [B*T, Dm]
+            ops.linear_tc(curS, w["motion_layer.w2"], M, Dm, D, y=out, bias=w["motion_layer.b"], ymap=(S, T, -(2 + G)), ldy=Dm)
         return out

@@ -68,3 +68,66 @@ def allreduce_flat_(bufs: List[torch.Tensor], group=None) -> int:
         for b in bufs:
             dist.all_reduce(b, op=dist.ReduceOp.SUM, group=group)
     return world
+
+
+class ChunkedGradExchange:
+    """Gradient all-reduce overlapped with backward (the reference gets the overlap from DistributedDataParallel's
+    buckets, train_ddp.py:63-65).  Every flat gradient buffer is cut into `chunks` contiguous pieces of whole parameters; a
+    post-accumulate-grad hook on each parameter counts its piece down, and the piece's SUM all-reduce is launched
+    asynchronously the moment its last gradient has been accumulated (NCCL runs it on its own stream, under the rest of
+    backward).  Backward produces gradients in roughly reverse registration order, so the LAST piece goes first.
+    `begin()` arms the hooks for the next backward — only the FINAL backward of a step: an all-reduce is linear, so a piece
+    that was reduced early must not receive further local gradients.  `finish()` launches the pieces that never completed
+    (parameters that received no gradient: `find_unused_parameters=True` in the reference), waits, and returns the world size.
+    `flats`: [(flat_grad, params, offsets, numel)] with every p.grad a view of flat_grad at its offset."""
+
+    def __init__(self, flats, chunks: int = 3, group=None):
+        self.group, self.armed, self.chunks, self.handles = group, False, [], []
+        for g, ps, offs, n in flats:
+            per = (n + chunks - 1) // chunks
+            lo_i = 0
+            while lo_i < len(ps):
+                hi_i = lo_i
+                while hi_i < len(ps) and offs[hi_i] - offs[lo_i] < per:
+                    hi_i += 1
+                hi = offs[hi_i] if hi_i < len(ps) else n
+                self.chunks.append(dict(view=g[offs[lo_i]:hi], params=ps[lo_i:hi_i], pending=hi_i - lo_i, work=None, early=False))
+                lo_i = hi_i
+        for c in self.chunks:
+            for prm in c["params"]:
+                self.handles.append(prm.register_post_accumulate_grad_hook(self._hook(c)))
+
+    def _world(self) -> int:
+        return dist.get_world_size(self.group) if dist.is_initialized() else 1
+
+    def _hook(self, c):
+        def hook(_param):
+            if not self.armed:
+                return
+            c["pending"] -= 1
+            if c["pending"] == 0 and self._world() > 1:
+                c["work"] = dist.all_reduce(c["view"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                c["early"] = True
+        return hook
+
+    def begin(self):
+        for c in self.chunks:
+            c["work"], c["pending"], c["early"] = None, len(c["params"]), False
+        self.armed = True
+
+    def finish(self) -> int:
+        self.armed = False
+        world = self._world()
+        if world > 1:
+            for c in self.chunks:
+                if c["work"] is None:
+                    c["work"] = dist.all_reduce(c["view"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            for c in self.chunks:
+                c["work"].wait()   # the current stream waits for the collective's stream
+                c["work"] = None
+        return world
+
+    def remove(self):
+        for h in self.handles:
+            h.remove()
+        self.handles = []

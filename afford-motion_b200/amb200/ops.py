@@ -118,11 +118,16 @@ def mha_fwd(qkv, out, key_pad_u8, B, S, H, hd, scale, out2=None):
     return out
 
 
-def mha_tc_fwd(qkv2, out, out2, key_pad_u8, B, S, H, hd, scale):
-    """tcgen05 attention on the bf16 (hi|lo) QKV written by the in_proj GEMM (see am_mha_tc_fwd)."""
+def mha_tc_fwd(qkv2, out, out2, key_pad_u8, B, S, H, hd, scale, q_row0=0):
+    """tcgen05 attention on the bf16 (hi|lo) QKV written by the in_proj GEMM (see am_mha_tc_fwd); q_row0 > 0: only the query rows
+    [q_row0, S) of every sample, written compactly (am_mha_tc_fwd_rows)."""
     _chk_cuda(qkv2)
-    _l.check(_l.load().am_mha_tc_fwd(_ptr(qkv2), _ptr(out), _ptr(out2), _ptr(key_pad_u8), B, S, H, hd, float(scale), _stream()),
-             "am_mha_tc_fwd")
+    if q_row0:
+        _l.check(_l.load().am_mha_tc_fwd_rows(_ptr(qkv2), _ptr(out), _ptr(out2), _ptr(key_pad_u8), B, S, H, hd, float(scale), int(q_row0),
+                                              _stream()), "am_mha_tc_fwd_rows")
+    else:
+        _l.check(_l.load().am_mha_tc_fwd(_ptr(qkv2), _ptr(out), _ptr(out2), _ptr(key_pad_u8), B, S, H, hd, float(scale), _stream()),
+                 "am_mha_tc_fwd")
     return out if out is not None else out2
 
 

@@ -128,9 +128,27 @@ class FusedAdamW(torch.optim.Optimizer):
         return [f["g"] for f in self._flat if f is not None]
 
     def all_reduce_grads(self, group: Optional[dist.ProcessGroup] = None):
-        """Data-parallel gradient exchange: ONE all-reduce(sum) per flat buffer (48.8 MB for CMDM); the division by the
-        world size is folded into the next fused step (`grad_scale`), so the mean costs no extra pass over the buffer."""
-        from .dist import allreduce_flat_
-        world = allreduce_flat_(self.flat_grads(), group)
+        """Data-parallel gradient exchange: all-reduce(sum) of the flat buffer (48.8 MB for CMDM); the division by the
+        world size is folded into the next fused step (`grad_scale`), so the mean costs no extra pass over the buffer.
+        After `begin_overlap()` the pieces whose gradients were complete during backward are already in flight: this call
+        launches the rest (pieces holding parameters that received no gradient) and waits for all of them."""
+        ov = getattr(self, "_overlap", None)
+        if ov is not None and ov.armed:
+            world = ov.finish()
+        else:
+            from .dist import allreduce_flat_
+            world = allreduce_flat_(self.flat_grads(), group)
         self._pending_scale = 1.0 / world
         return world
+
+    # ---- exchange overlapped with backward (train_ddp.py:63-65 gets this from DDP's buckets)
+    def enable_overlap(self, chunks: int = 3, group: Optional[dist.ProcessGroup] = None) -> int:
+        """Hook the parameters so that pieces of the flat gradient buffer are all-reduced while backward is still running
+        (`amb200.dist.ChunkedGradExchange`).  Call `begin_overlap()` before the final backward of a step and
+        `all_reduce_grads()` after it, as before.  Returns the number of pieces."""
+        from .dist import ChunkedGradExchange
+        self._overlap = ChunkedGradExchange([(f["g"], f["params"], f["offs"], f["n"]) for f in self._flat if f is not None], chunks, group)
+        return len(self._overlap.chunks)
+
+    def begin_overlap(self):
+        self._overlap.begin()

@@ -43,6 +43,7 @@ struct AttParams {
     __nv_bfloat16* out2;      // [B*S, 2*H*64] bf16 (hi | lo) or NULL
     long long* dbg;           // optional clock64 timeline of CTA 0 (tools/att_timeline.py)
     int fast;                 // am_set_precision(1): single bf16 pass (Q_hi K_hi^T, P_hi V_hi); the lo tiles are not even loaded
+    int q0;                   // first query row computed per sample (pipelined kernel only); outputs hold S - q0 rows per sample
 };
 
 __device__ __forceinline__ uint32_t smem_u32a(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -479,6 +480,18 @@ __device__ __forceinline__ void tmem_ld32_wait(uint32_t r[32]) {
         :: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t r[32]) {   // columns [0,16) into r[0..15]
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st8a(uint32_t taddr, const uint32_t r[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 mha_tc_pipe_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tmo, AttParams p) {
     pdl_launch_dependents();
@@ -495,18 +508,21 @@ mha_tc_pipe_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
     uint64_t* p_ready = bars + 11;  // [12] one per 32-key chunk of P
     uint64_t* stage_full = bars + 23;   // 256 arrivals: O of the tile is staged (bf16 hi | lo) in the Q buffer
     uint64_t* q_free = bars + 24;       // the TMA store has read the staged tile: Q of the tile after next may be loaded
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 25);
-    uint32_t* maskbits = tmem_holder + 1;  // [12] bit k of word w: key 32w+k is attendable
+    uint64_t* pv_done = bars + 25;      // [3] P V of key tile kt has completed: S of the next query tile may overwrite its columns
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 28);
     float* xmax = reinterpret_cast<float*>(smem + OFF_BAR + 256);   // [2][128]
     float* xsum = xmax + 256;                                         // [2][128]
-    if (smem - smem_raw > 768) __trap();   // the 1024-byte round-up above may use at most the 768 bytes of slack in ATT_SMEM
+    uint32_t* maskbits = reinterpret_cast<uint32_t*>(xsum + 256);     // [12] bit k of word w: key 32w+k is attendable
+    if (smem - smem_raw > 704) __trap();   // the 1024-byte round-up above may use at most the slack left in ATT_SMEM (768 - 64 for the mask)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
     const int S = p.S, D = p.H * HD;
-    const int nq = (S + QT - 1) / QT;
-    const int nblk = (S + 63) / 64;
+    const int So = S - p.q0;              // query rows computed (and written, compactly) per sample: rows [q0, S)
+    const int nq = (So + QT - 1) / QT;
     const int nkt = (S + KT - 1) / KT;
+    const int nch = (S + 31) >> 5;                        // 32-key chunks holding at least one key
+    const bool tail16 = S - (nch - 1) * 32 <= 16;        // the last chunk is handled as 16 columns / one k-step
 
     if (warp == 10 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm)) : "memory");
@@ -517,6 +533,7 @@ mha_tc_pipe_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
         mbar_init_a(v_full, 1); mbar_init_a(q_full, 1); mbar_init_a(q_empty, 1); mbar_init_a(o_full, 1);
         mbar_init_a(o_free, 256);
         mbar_init_a(stage_full, 256); mbar_init_a(q_free, 1);
+        for (int j = 0; j < 3; ++j) mbar_init_a(&pv_done[j], 1);
         for (int j = 0; j < 12; ++j) mbar_init_a(&p_ready[j], 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -554,8 +571,8 @@ mha_tc_pipe_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
             auto produce = [&](auto fc) {
                 constexpr bool FAST = decltype(fc)::value;
                 mbar_expect_tx_a(q_full, (FAST ? 1 : 2) * TILE_BYTES);
-                tma_load_3d(smem + OFF_QH, &tm, q_full, h * HD, 0, b);
-                if (!FAST) tma_load_3d(smem + OFF_QL, &tm, q_full, 3 * D + h * HD, 0, b);
+                tma_load_3d(smem + OFF_QH, &tm, q_full, h * HD, p.q0, b);
+                if (!FAST) tma_load_3d(smem + OFF_QL, &tm, q_full, 3 * D + h * HD, p.q0, b);
                 for (int kt = 0; kt < NKT; ++kt) {
                     mbar_expect_tx_a(&k_full[kt], (FAST ? 1 : 2) * TILE_BYTES);
                     tma_load_3d(smem + OFF_KH + kt * TILE_BYTES, &tm, &k_full[kt], D + h * HD, kt * KT, b);
@@ -571,100 +588,119 @@ mha_tc_pipe_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
                     // once the TMA store of tile t-2 has read its staged O (the epilogue staged it after S of tile t-1 was complete)
                     if (t == 1) mbar_wait_a(q_empty, 0); else mbar_wait_a(q_free, (t - 2) & 1);
                     mbar_expect_tx_a(q_full, (FAST ? 1 : 2) * TILE_BYTES);
-                    tma_load_3d(smem + OFF_QH, &tm, q_full, h * HD, t * QT, b);
-                    if (!FAST) tma_load_3d(smem + OFF_QL, &tm, q_full, 3 * D + h * HD, t * QT, b);
+                    tma_load_3d(smem + OFF_QH, &tm, q_full, h * HD, p.q0 + t * QT, b);
+                    if (!FAST) tma_load_3d(smem + OFF_QL, &tm, q_full, 3 * D + h * HD, p.q0 + t * QT, b);
                 }
             };
             if (p.fast) produce(std::true_type{}); else produce(std::false_type{});
         }
-    } else if (warp == 11) {
-        // ===================== MMA issuer (whole warp, elect.sync per instruction) =====================
-        {
-            auto issue = [&](auto fc) {
-                constexpr bool FAST = decltype(fc)::value;
-                const uint32_t sb = smem_u32a(smem);
-                const uint64_t qh = desc_kmajor(sb + OFF_QH), ql = desc_kmajor(sb + OFF_QL);
-                // keys of the last key tile rounded up to the MMA's N granularity (16): S = 326 -> 80 columns instead of 128.  The
-                // columns beyond are never written; the key mask keeps the softmax away from them.
-                const int n_last = min(KT, ((S - (nkt - 1) * KT + 15) >> 4) << 4);
-                // S(t)[:, 128 kt0 : 128 kt0 + ncols] = Q K^T, 3-term split.  Consecutive K tiles are contiguous in shared memory
-                // (8-row groups 1024 B apart throughout), so key tiles 0 and 1 are ONE N = 256 operand.
-                auto qk = [&](int kt0, int ncols) {
-                    const uint64_t kh = desc_kmajor(sb + OFF_KH + kt0 * TILE_BYTES), kl = desc_kmajor(sb + OFF_KL + kt0 * TILE_BYTES);
-                    const uint32_t d = tmem_base + S_COL + kt0 * KT;
-                    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ncols >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    } else if (warp == 8) {
+        // ===================== S = Q K^T issuer (whole warp, elect.sync per instruction) =====================
+        // Two issuing warps: this one for Q K^T, warp 11 for P V.  A single issuer was the pacing resource — it shares its scheduler
+        // with two softmax warps and spends ~60-110 cycles per MMA against a 32-64 cycle tensor floor, 84 MMAs per query tile.
+        // Ordering between the two streams goes through mbarriers: S(t+1) of key tile kt may only overwrite the P(t) columns once
+        // P V of that key tile has COMPLETED (pv_done[kt], a tcgen05.commit of the P V warp).
+        auto issue = [&](auto fc) {
+            constexpr bool FAST = decltype(fc)::value;
+            const uint32_t sb = smem_u32a(smem);
+            const uint64_t qh = desc_kmajor(sb + OFF_QH), ql = desc_kmajor(sb + OFF_QL);
+            // keys of the last key tile rounded up to the MMA's N granularity (16): S = 326 -> 80 columns instead of 128.  The
+            // columns beyond are never written; the key mask keeps the softmax away from them.
+            const int n_last = min(KT, ((S - (nkt - 1) * KT + 15) >> 4) << 4);
+            // S(t)[:, 128 kt : 128 kt + ncols] = Q K_kt^T, 3-term split
+            auto qk = [&](int kt, int ncols) {
+                const uint64_t kh = desc_kmajor(sb + OFF_KH + kt * TILE_BYTES), kl = desc_kmajor(sb + OFF_KL + kt * TILE_BYTES);
+                const uint32_t d = tmem_base + S_COL + kt * KT;
+                const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ncols >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 #pragma unroll
-                    for (int k = 0; k < HD / 16; ++k) {
-                        const uint64_t ko = (uint64_t)(k * 2);
-                        if (FAST) { umma_ss_w(d, qh + ko, kh + ko, idesc, k ? 1u : 0u); continue; }
-                        umma_ss_w(d, ql + ko, kh + ko, idesc, k ? 1u : 0u);
-                        umma_ss_w(d, qh + ko, kl + ko, idesc, 1u);
-                        umma_ss_w(d, qh + ko, kh + ko, idesc, 1u);
-                    }
-                };
-                // prologue: S of tile 0, each key tile as soon as its K tile has landed
-                mbar_wait_a(q_full, 0);
-                if (dbg && lane == 0) p.dbg[8] = clock64();
+                for (int k = 0; k < HD / 16; ++k) {
+                    const uint64_t ko = (uint64_t)(k * 2);
+                    if (FAST) { umma_ss_w(d, qh + ko, kh + ko, idesc, k ? 1u : 0u); continue; }
+                    umma_ss_w(d, ql + ko, kh + ko, idesc, k ? 1u : 0u);
+                    umma_ss_w(d, qh + ko, kl + ko, idesc, 1u);
+                    umma_ss_w(d, qh + ko, kh + ko, idesc, 1u);
+                }
+                umma_commit_w(&s_full[kt]);
+            };
+            // tile 0: each key tile as soon as its K tile has landed
+            mbar_wait_a(q_full, 0);
+            if (dbg && lane == 0) p.dbg[8] = clock64();
+            for (int kt = 0; kt < nkt; ++kt) {
+                mbar_wait_a(&k_full[kt], 0);
+                if (dbg && lane == 0 && kt == 0) p.dbg[1] = clock64();
+                fence_after_a();
+                qk(kt, kt == nkt - 1 ? n_last : KT);
+            }
+            umma_commit_w(q_empty);
+            if (dbg && lane == 0) p.dbg[16] = clock64();
+            // tile t+1 behind P V of tile t, key tile by key tile
+            for (int t = 1; t < nq; ++t) {
+                mbar_wait_a(q_full, t & 1);
+                if (dbg && lane == 0) p.dbg[8 + t] = clock64();
                 for (int kt = 0; kt < nkt; ++kt) {
-                    mbar_wait_a(&k_full[kt], 0);
-                    if (dbg && lane == 0 && kt == 0) p.dbg[1] = clock64();
+                    mbar_wait_a(&pv_done[kt], (t - 1) & 1);
                     fence_after_a();
                     qk(kt, kt == nkt - 1 ? n_last : KT);
-                    umma_commit_w(&s_full[kt]);
+                    if (dbg && lane == 0 && t == 2) p.dbg[88 + kt] = clock64();
                 }
-                umma_commit_w(q_empty);
-                if (dbg && lane == 0) p.dbg[16] = clock64();
-                mbar_wait_a(v_full, 0);
-                for (int t = 0; t < nq; ++t) {
-                    const uint32_t pt = t & 1;
-                    const bool more = t + 1 < nq;
-                    for (int kt = 0; kt < nkt; ++kt) {
-                        // the two softmax groups work on blocks 2 kt and 2 kt + 1 side by side: consume their 32-key chunks alternately
+                if (dbg && lane == 0) p.dbg[16 + t] = clock64();
+            }
+        };
+        if (p.fast) issue(std::true_type{}); else issue(std::false_type{});
+    } else if (warp == 11) {
+        // ===================== O = P V issuer (whole warp, elect.sync per instruction) =====================
+        auto issue = [&](auto fc) {
+            constexpr bool FAST = decltype(fc)::value;
+            const uint32_t sb = smem_u32a(smem);
+            // Every instruction this warp spends between two MMAs delays the tensor pipe (it shares its scheduler with two softmax
+            // warps): the V descriptors and the P address advance by constants (32 keys = 4096 B of V rows = +256 in the descriptor's
+            // 16-byte address field, 32 TMEM columns).
+            const uint64_t vhl0 = desc_mnmajor_hilo(sb + OFF_VH), vh0 = desc_mnmajor(sb + OFF_VH);
+            mbar_wait_a(v_full, 0);
+            for (int t = 0; t < nq; ++t) {
+                const uint32_t pt = t & 1;
+                const bool more = t + 1 < nq;
+                for (int kt = 0; kt < nkt; ++kt) {
+                    // The two softmax groups work on the 64-key blocks 2 kt and 2 kt + 1 side by side, each chunk by chunk: consume
+                    // chunks 4 kt + {0, 2, 1, 3} in the order they are produced.  (Assigning CHUNKS alternately to the groups
+                    // balances a short last block better but measured slower: 45.9 vs 41.7 us per launch.)
+                    const uint64_t vhl_kt = vhl0 + (uint64_t)(kt * 1024), vh_kt = vh0 + (uint64_t)(kt * 1024);
+                    const uint32_t a_kt = tmem_base + S_COL + kt * 128;
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const int j = 2 * kt + (c & 1), hlf = c >> 1;
-                            if (j >= nblk) continue;
-                            mbar_wait_a(&p_ready[2 * j + hlf], pt);
-                            if (kt == 0 && c == 0 && t > 0) mbar_wait_a(o_free, (t - 1) & 1);   // the epilogue of tile t-1 has read O
-                            fence_after_a();
-                            if (dbg && lane == 0 && t == 1) p.dbg[64 + 2 * j + hlf] = clock64();
-                            const uint32_t voff = (uint32_t)(j * 64) * 128u;
-#pragma unroll
-                            for (int kk = 0; kk < 2; ++kk) {
-                                // 16 keys per MMA; P_hi words of chunk (j, hlf) at column 64 j + 32 hlf + 8 kk, P_lo 16 columns further
-                                const int k = 2 * hlf + kk;
-                                const uint32_t a_hi = tmem_base + S_COL + j * 64 + hlf * 32 + kk * 8, a_lo = a_hi + 16;
-                                const uint64_t vhl = desc_mnmajor_hilo(sb + OFF_VH + voff + k * 2048), vh = desc_mnmajor(sb + OFF_VH + voff + k * 2048);
-                                const uint32_t acc = (kt | c | kk) ? 1u : 0u;
-                                if (FAST) { umma_ts_w(tmem_base + O_COL, a_hi, vh, IDESC_PV, acc); continue; }
-                                umma_ts_w(tmem_base + O_COL, a_hi, vhl, IDESC_PV2, acc);
-                                umma_ts_w(tmem_base + O_COL, a_lo, vh, IDESC_PV, 1u);
+                    for (int e = 0; e < 4; ++e) {
+                        const int cc = ((e & 1) << 1) | (e >> 1);   // 0, 2, 1, 3
+                        const int c = 4 * kt + cc;
+                        if (c >= nch) continue;
+                        mbar_wait_a(&p_ready[c], pt);
+                        if (kt == 0 && e == 0 && t > 0) mbar_wait_a(o_free, (t - 1) & 1);   // the epilogue of tile t-1 has read O
+                        fence_after_a();
+                        if (dbg && lane == 0 && t == 1) p.dbg[64 + c] = clock64();
+                        // 16 keys per MMA: P_hi words at column a (+8 for the second k-step), P_lo 16 columns further; V rows 16 further = +128
+                        const uint32_t a = a_kt + cc * 32;
+                        const uint64_t vhl = vhl_kt + (uint64_t)(cc * 256), vh = vh_kt + (uint64_t)(cc * 256);
+                        const bool two = c != nch - 1 || !tail16;   // a last chunk of <= 16 keys is one k-step
+                        const uint32_t acc = (kt | e) ? 1u : 0u;
+                        if (FAST) {
+                            umma_ts_w(tmem_base + O_COL, a, vh, IDESC_PV, acc);
+                            if (two) umma_ts_w(tmem_base + O_COL, a + 8, vh + 128, IDESC_PV, 1u);
+                        } else {
+                            umma_ts_w(tmem_base + O_COL, a, vhl, IDESC_PV2, acc);
+                            umma_ts_w(tmem_base + O_COL, a + 16, vh, IDESC_PV, 1u);
+                            if (two) {
+                                umma_ts_w(tmem_base + O_COL, a + 8, vhl + 128, IDESC_PV2, 1u);
+                                umma_ts_w(tmem_base + O_COL, a + 24, vh + 128, IDESC_PV, 1u);
                             }
-                        }
-                        if (dbg && lane == 0 && t == 1) p.dbg[80 + kt] = clock64();
-                        if (kt == nkt - 1) {
-                            umma_commit_w(o_full);
-                            if (dbg && lane == 0) p.dbg[24 + t] = clock64();
-                        }
-                        // the P columns of key tile kt are consumed (tcgen05.mma executes in issue order) -> S of the NEXT query tile
-                        // may overwrite them.  One N = 128 MMA group per key tile (merging tiles 0 and 1 into N = 256 saved 12 MMAs but
-                        // held back P V of key tile 2, which gates the epilogue).
-                        if (more) {
-                            if (kt == 0) {
-                                mbar_wait_a(q_full, (t + 1) & 1);
-                                fence_after_a();
-                                if (dbg && lane == 0) p.dbg[8 + t + 1] = clock64();
-                            }
-                            qk(kt, kt == nkt - 1 ? n_last : KT);
-                            umma_commit_w(&s_full[kt]);
-                            if (dbg && lane == 0 && t == 1) p.dbg[88 + kt] = clock64();
-                            if (dbg && lane == 0 && kt == nkt - 1) p.dbg[16 + t + 1] = clock64();
                         }
                     }
+                    if (more) umma_commit_w(&pv_done[kt]);   // the P columns of key tile kt are consumed
+                    if (kt == nkt - 1) {
+                        umma_commit_w(o_full);
+                        if (dbg && lane == 0) p.dbg[24 + t] = clock64();
+                    }
                 }
-            };
-            if (p.fast) issue(std::true_type{}); else issue(std::false_type{});
-        }
+            }
+        };
+        if (p.fast) issue(std::true_type{}); else issue(std::false_type{});
     } else if (warp == 9) {
         // ===================== O store: TMA store of the staged tile =====================
         if (lane == 0) {
@@ -690,80 +726,104 @@ mha_tc_pipe_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
         const float sc2 = p.scale * 1.4426950408889634f;
         uint32_t va[32], vb[32];
 
-        // row max of the raw scores of tile t over this group's blocks, tcgen05.ld one chunk ahead of the fmax chain
-        auto chunk_max = [&](const uint32_t (&v)[32], int j, int hlf, float mx) {
-            const uint32_t mb = maskbits[2 * j + hlf];
+        // ---- chunk helpers.  Chunk c = keys [32 c, 32 c + 32) = S columns [32 c, 32 c + 32); a 64-key block is two chunks.  A last
+        // chunk with <= 16 keys (S = 326: 6 keys) is loaded / processed / stored as 16 columns.
+        auto ld_issue = [&](uint32_t (&v)[32], int c) {
+            if (c == nch - 1 && tail16) tmem_ld16_issue(lane_addr + S_COL + c * 32, v);
+            else tmem_ld32_issue(lane_addr + S_COL + c * 32, v);
+        };
+        auto chunk_max = [&](const uint32_t (&v)[32], int c, float mx) {
+            const uint32_t mb = maskbits[c];
             if (mb == 0xffffffffu) {
 #pragma unroll
-                for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(v[c]));
+                for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(v[e]));
+            } else if (c == nch - 1 && tail16) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                    if ((mb >> e) & 1u) mx = fmaxf(mx, __uint_as_float(v[e]));
             } else {
 #pragma unroll
-                for (int c = 0; c < 32; ++c)
-                    if ((mb >> c) & 1u) mx = fmaxf(mx, __uint_as_float(v[c]));
+                for (int e = 0; e < 32; ++e)
+                    if ((mb >> e) & 1u) mx = fmaxf(mx, __uint_as_float(v[e]));
             }
             return mx;
         };
-        // blocks [jlo, jhi) of this group (every other block starting at grp)
+        // row max of the raw scores of tile t over this group's 64-key blocks in [jlo, jhi) (block j = chunks 2 j, 2 j + 1; group g owns
+        // the blocks j % 2 == g), tcgen05.ld one chunk ahead of the fmax chain
         auto pass1 = [&](int t, int jlo, int jhi, float mx) {
             const uint32_t pt = t & 1;
-            int j = grp;
-            while (j < jlo) j += 2;
+            int j = jlo + ((jlo ^ grp) & 1);
             if (j >= jhi) return mx;
             mbar_wait_a(&s_full[j >> 1], pt);
             fence_after_a();
             if (dbg && threadIdx.x == 0 && jlo == 0) p.dbg[32 + t] = clock64();
-            tmem_ld32_issue(lane_addr + S_COL + j * 64, va);
+            ld_issue(va, 2 * j);
             for (; j < jhi; j += 2) {
+                const int c0 = 2 * j, c1 = c0 + 1, jn = j + 2;
+                const bool has1 = c1 < nch;
                 tmem_ld32_wait(va);
-                tmem_ld32_issue(lane_addr + S_COL + j * 64 + 32, vb);
-                mx = chunk_max(va, j, 0, mx);
-                tmem_ld32_wait(vb);
-                const int jn = j + 2;
+                if (has1) ld_issue(vb, c1);
+                mx = chunk_max(va, c0, mx);
+                if (has1) tmem_ld32_wait(vb);
                 bool pre = false;
                 if (jn < jhi && mbar_test_a(&s_full[jn >> 1], pt)) {   // next block's key tile already complete: prefetch under the fmax chain
                     fence_after_a();
-                    tmem_ld32_issue(lane_addr + S_COL + jn * 64, va);
+                    ld_issue(va, 2 * jn);
                     pre = true;
                 }
-                mx = chunk_max(vb, j, 1, mx);
+                if (has1) mx = chunk_max(vb, c1, mx);
                 if (jn < jhi && !pre) {
                     mbar_wait_a(&s_full[jn >> 1], pt);
                     fence_after_a();
-                    tmem_ld32_issue(lane_addr + S_COL + jn * 64, va);
+                    ld_issue(va, 2 * jn);
                 }
             }
             return mx;
         };
-        // p = 2^(s*sc2 - mx2) of one 32-key chunk -> packed bf16 hi words [0,16) | lo words [16,32) of the chunk's own columns
-        auto chunk_exp = [&](const uint32_t (&v)[32], int j, int hlf, float mx2, float& sum) {
-            const uint32_t mb = maskbits[2 * j + hlf];
-            uint32_t ph[16], pl[16];
-            if (mb == 0xffffffffu) {
+        // p = 2^(s*sc2 - mx2) of one chunk -> packed bf16 hi words [0,16) | lo words [16,32) of the chunk's own columns
+        auto chunk_exp = [&](const uint32_t (&v)[32], int c, float mx2, float& sum) {
+            const uint32_t mb = maskbits[c];
+            if (c == nch - 1 && tail16) {
+                uint32_t ph[8], pl[8];
 #pragma unroll
-                for (int c = 0; c < 32; c += 2) {
-                    const float e0 = ex2_approx(fmaf(__uint_as_float(v[c]), sc2, -mx2));
-                    const float e1 = ex2_approx(fmaf(__uint_as_float(v[c + 1]), sc2, -mx2));
+                for (int e = 0; e < 16; e += 2) {
+                    const float e0 = ((mb >> e) & 1u) ? ex2_approx(fmaf(__uint_as_float(v[e]), sc2, -mx2)) : 0.f;
+                    const float e1 = ((mb >> (e + 1)) & 1u) ? ex2_approx(fmaf(__uint_as_float(v[e + 1]), sc2, -mx2)) : 0.f;
                     sum += e0 + e1;
-                    split_pair(e0, e1, ph[c / 2], pl[c / 2]);
+                    split_pair(e0, e1, ph[e / 2], pl[e / 2]);
                 }
+                tmem_st8a(lane_addr + S_COL + c * 32, ph);
+                tmem_st8a(lane_addr + S_COL + c * 32 + 16, pl);
             } else {
+                uint32_t ph[16], pl[16];
+                if (mb == 0xffffffffu) {
 #pragma unroll
-                for (int c = 0; c < 32; c += 2) {
-                    const float e0 = ((mb >> c) & 1u) ? ex2_approx(fmaf(__uint_as_float(v[c]), sc2, -mx2)) : 0.f;
-                    const float e1 = ((mb >> (c + 1)) & 1u) ? ex2_approx(fmaf(__uint_as_float(v[c + 1]), sc2, -mx2)) : 0.f;
-                    sum += e0 + e1;
-                    split_pair(e0, e1, ph[c / 2], pl[c / 2]);
+                    for (int e = 0; e < 32; e += 2) {
+                        const float e0 = ex2_approx(fmaf(__uint_as_float(v[e]), sc2, -mx2));
+                        const float e1 = ex2_approx(fmaf(__uint_as_float(v[e + 1]), sc2, -mx2));
+                        sum += e0 + e1;
+                        split_pair(e0, e1, ph[e / 2], pl[e / 2]);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; e += 2) {
+                        const float e0 = ((mb >> e) & 1u) ? ex2_approx(fmaf(__uint_as_float(v[e]), sc2, -mx2)) : 0.f;
+                        const float e1 = ((mb >> (e + 1)) & 1u) ? ex2_approx(fmaf(__uint_as_float(v[e + 1]), sc2, -mx2)) : 0.f;
+                        sum += e0 + e1;
+                        split_pair(e0, e1, ph[e / 2], pl[e / 2]);
+                    }
                 }
+                tmem_st16a(lane_addr + S_COL + c * 32, ph);
+                tmem_st16a(lane_addr + S_COL + c * 32 + 16, pl);
             }
-            tmem_st16a(lane_addr + S_COL + j * 64 + hlf * 32, ph);
-            tmem_st16a(lane_addr + S_COL + j * 64 + hlf * 32 + 16, pl);
             tmem_wait_st();
             fence_before_a();
-            mbar_arrive_a(&p_ready[2 * j + hlf]);
+            mbar_arrive_a(&p_ready[c]);
         };
 
+        const int nblk = (nch + 1) >> 1;      // 64-key blocks holding at least one key
         float mx_own = pass1(0, 0, nblk, -CUDART_INF_F);
-        const int jsplit = min(nblk, 4);   // blocks of key tiles 0, 1 | key tile 2
+        const int jsplit = min(nblk, 4);      // blocks of key tiles 0, 1 | key tile 2
         for (int t = 0; t < nq; ++t) {
             const uint32_t pt = t & 1;
             const int qi = t * QT + r;
@@ -773,18 +833,20 @@ mha_tc_pipe_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
             if (dbg && threadIdx.x == 0) p.dbg[40 + t] = clock64();
             // pass 2
             float sum = 0.f;
-            if (grp < nblk) tmem_ld32_issue(lane_addr + S_COL + grp * 64, va);
+            if (grp < nblk) ld_issue(va, 2 * grp);
             for (int j = grp; j < nblk; j += 2) {
+                const int c0 = 2 * j, c1 = c0 + 1;
+                const bool has1 = c1 < nch;
                 tmem_ld32_wait(va);
-                tmem_ld32_issue(lane_addr + S_COL + j * 64 + 32, vb);
-                chunk_exp(va, j, 0, mx2, sum);
-                tmem_ld32_wait(vb);
-                if (j + 2 < nblk) tmem_ld32_issue(lane_addr + S_COL + (j + 2) * 64, va);
-                chunk_exp(vb, j, 1, mx2, sum);
+                if (has1) ld_issue(vb, c1);
+                chunk_exp(va, c0, mx2, sum);
+                if (has1) tmem_ld32_wait(vb);
+                if (j + 2 < nblk) ld_issue(va, 2 * (j + 2));
+                if (has1) chunk_exp(vb, c1, mx2, sum);
                 if (dbg && t == 1 && (threadIdx.x & 127) == 0) p.dbg[96 + j] = clock64();
             }
             if (dbg && threadIdx.x == 0) p.dbg[48 + t] = clock64();
-            // row max of the NEXT tile over key tiles 0, 1 (their S is complete: it was issued behind P V of blocks 0-3) while the
+            // row max of the NEXT tile over key tiles 0, 1 (their S is complete: it was issued behind P V of chunks 0-7) while the
             // tensor pipe finishes P V of this tile and S of key tile 2
             if (t + 1 < nq) mx_own = pass1(t + 1, 0, jsplit, -CUDART_INF_F);
             xsum[grp * 128 + r] = sum;
@@ -808,9 +870,9 @@ mha_tc_pipe_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
             fence_before_a();
             mbar_arrive_a(o_free);
             if (dbg && (threadIdx.x & 127) == 0) p.dbg[104 + 4 * t + grp] = clock64();
-            if (qi < S) {
+            if (qi < So) {
                 const float inv = 1.0f / sum;
-                const int64_t row = (int64_t)b * S + qi;
+                const int64_t row = (int64_t)b * So + qi;
                 if (p.out) {
                     float* dst = p.out + row * D + h * HD + grp * 32;
 #pragma unroll
@@ -860,9 +922,10 @@ typedef CUresult (*EncodeTiledFnA)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
 static long long* g_att_dbg = nullptr;
 extern "C" void am_att_set_debug_(void* buf) { g_att_dbg = reinterpret_cast<long long*>(buf); }  // debug hook, not in the public header
 
-extern "C" int am_mha_tc_fwd(const void* qkv2, float* out, void* out2, const uint8_t* key_pad, int B, int S, int H, int hd, float scale,
-                             am_stream_t stream) {
+extern "C" int am_mha_tc_fwd_rows(const void* qkv2, float* out, void* out2, const uint8_t* key_pad, int B, int S, int H, int hd, float scale,
+                                  int q_row0, am_stream_t stream) {
     AM_REQUIRE(qkv2 && (out || out2) && B > 0 && S > 0 && H > 0, AM_EINVAL, "am_mha_tc_fwd: bad args");
+    AM_REQUIRE(q_row0 >= 0 && q_row0 < S, AM_EINVAL, "am_mha_tc_fwd_rows: q_row0 must be in [0, S)");
     AM_REQUIRE(hd == HD, AM_EINVAL, "am_mha_tc_fwd: head dim must be 64");
     AM_REQUIRE(S <= NKT * KT, AM_EINVAL, "am_mha_tc_fwd: S must be <= 384 (whole key row lives in TMEM)");
     AM_REQUIRE((reinterpret_cast<uintptr_t>(qkv2) & 15u) == 0 && (!out || (reinterpret_cast<uintptr_t>(out) & 15u) == 0) &&
@@ -900,12 +963,13 @@ extern "C" int am_mha_tc_fwd(const void* qkv2, float* out, void* out2, const uin
         }
         attr = true;
     }
-    AttParams p{B, S, H, scale, key_pad, out, reinterpret_cast<__nv_bfloat16*>(out2), g_att_dbg, am_get_precision()};
+    AM_REQUIRE(pipe || q_row0 == 0, AM_EINVAL, "am_mha_tc_fwd_rows: q_row0 > 0 needs the pipelined kernel (AMB200_ATTN_PIPE=0 is set)");
+    AttParams p{B, S, H, scale, key_pad, out, reinterpret_cast<__nv_bfloat16*>(out2), g_att_dbg, am_get_precision(), q_row0};
     CUtensorMap tmo = tm;   // store map of the bf16 (hi | lo) output [B, S, 2 H 64]: 128-row x 64-column boxes, rows >= S clipped
     if (pipe && out2) {
         const uint64_t ocols = (uint64_t)2 * H * HD;
-        cuuint64_t odim[3] = {ocols, (cuuint64_t)S, (cuuint64_t)B};
-        cuuint64_t ostr[2] = {ocols * 2, ocols * 2 * (cuuint64_t)S};
+        cuuint64_t odim[3] = {ocols, (cuuint64_t)(S - q_row0), (cuuint64_t)B};
+        cuuint64_t ostr[2] = {ocols * 2, ocols * 2 * (cuuint64_t)(S - q_row0)};
         if (enc(&tmo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, out2, odim, ostr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
             am_set_error_("am_mha_tc_fwd: cuTensorMapEncodeTiled (output) failed");
@@ -916,4 +980,9 @@ extern "C" int am_mha_tc_fwd(const void* qkv2, float* out, void* out2, const uin
     else am_launch(mha_tc_kernel, dim3(B * H), dim3(ATT_THREADS), ATT_SMEM, as_stream(stream), 1, tm, p);
     AM_LAUNCH_CHECK("mha_tc_fwd");
     return AM_OK;
+}
+
+extern "C" int am_mha_tc_fwd(const void* qkv2, float* out, void* out2, const uint8_t* key_pad, int B, int S, int H, int hd, float scale,
+                             am_stream_t stream) {
+    return am_mha_tc_fwd_rows(qkv2, out, out2, key_pad, B, S, H, hd, scale, 0, stream);
 }

@@ -605,6 +605,8 @@ def main():
                 net = torch.nn.SyncBatchNorm.convert_sync_batchnorm(tmodel)
             net.train()
             opt = FusedAdamW([p for p in net.parameters() if p.requires_grad], lr=1e-4, weight_decay=0.0)
+            if world > 1:
+                opt.enable_overlap(3)   # the flat gradient buffer is all-reduced in 3 pieces as backward completes them
             h4 = dict(x0=synth.motion_noise(B, T, DM, seed=400 + rank).pin_memory(), xyz=synth.scene_points(B, NPTS, seed=400 + rank).pin_memory(),
                       contact=synth.contact_map(B, NPTS, seed=400 + rank).pin_memory(), x_mask=synth.motion_mask(B, T, seed=400 + rank).pin_memory())
             t4 = synth.text_features(B, seed=400 + rank).to(dev)
@@ -618,6 +620,8 @@ def main():
                 opt.zero_grad()
                 t = uniform_sampling(B, dev, tdiff.num_timesteps)
                 loss = tdiff.training_losses(net, d["x0"], t, model_kwargs=kw)["loss"].mean()
+                if world > 1:
+                    opt.begin_overlap()
                 loss.backward()
                 opt.all_reduce_grads()
                 opt.step()

@@ -288,6 +288,11 @@ int am_linear_ln_tc(const void* A2, const void* W2, int M, int N, int Kp, const 
  * Replaces the SDPA / native-MHA library call inside torch.nn.TransformerEncoderLayer (models/cmdm.py:66-77,167). */
 int am_mha_tc_fwd(const void* qkv2, float* out, void* out2, const uint8_t* key_pad, int B, int S, int H, int hd,
                   float scale, am_stream_t stream);
+/* Same, restricted to the query rows [q_row0, S) of every sample (all S keys are attended): out / out2 hold S - q_row0 rows per
+ * sample, compactly.  The last CMDM encoder layer only needs its motion tokens — the reference slices the layer's output
+ * (models/cmdm.py:183-186, `x[non_motion_token:]`) — so its attention, out_proj, feed-forward and LayerNorms run on those rows only. */
+int am_mha_tc_fwd_rows(const void* qkv2, float* out, void* out2, const uint8_t* key_pad, int B, int S, int H, int hd,
+                       float scale, int q_row0, am_stream_t stream);
 
 /* ------------------------------------------------------------------ training path (forward-with-statistics + backward)
  * fp32 SIMT building blocks of the CMDM training step (utils/training.py:141-154 -> diffusion training_losses ->

@@ -65,3 +65,60 @@ def test_shard_partitions_any_batch():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [e - s for s, e in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _overlap_worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "afford-motion_b200"))
+    import torch.distributed as dist
+    from amb200 import dist as D
+    D.init("gloo")
+    torch.manual_seed(0)
+    # five parameters whose gradients are views of ONE flat buffer, as amb200.optim.FusedAdamW lays them out; `unused` gets no gradient
+    shapes = [(7, 3), (5,), (4, 4), (9,), (2, 6)]
+    offs, n = [], 0
+    for sh in shapes:
+        offs.append(n)
+        n += (int(torch.tensor(sh).prod()) + 3) // 4 * 4
+    flat = torch.zeros(n)
+    ps = []
+    for sh, o in zip(shapes, offs):
+        prm = torch.nn.Parameter(torch.randn(*sh))
+        prm.grad = flat[o:o + prm.numel()].view(sh)
+        ps.append(prm)
+    ex = D.ChunkedGradExchange([(flat, ps, offs, n)], chunks=3)
+    x = torch.full((3,), float(rank + 1))
+    def loss_fn():
+        return (ps[0] @ x).sum() * (rank + 1) + (ps[1] ** 2).sum() + (ps[2] * (rank + 2)).sum() + (ps[4].sum() * 3.0)   # ps[3] unused
+    # reference: plain backward + one flat all-reduce
+    loss_fn().backward()
+    ref = flat.clone()
+    dist.all_reduce(ref)
+    flat.zero_()
+    # overlapped: hooks launch complete pieces during backward, finish() reduces the piece holding the unused parameter
+    ex.begin()
+    loss_fn().backward()
+    early = [c["early"] for c in ex.chunks]
+    wsz = ex.finish()
+    ok = wsz == world and torch.allclose(flat, ref) and any(early) and not all(early)
+    # a second step re-arms cleanly; an un-armed backward launches nothing
+    flat.zero_()
+    loss_fn().backward()
+    quiet = all(c["work"] is None for c in ex.chunks)
+    q.put((rank, bool(ok), bool(quiet), len(ex.chunks)))
+    dist.destroy_process_group()
+
+
+def test_chunked_grad_exchange_overlaps_and_matches_flat_allreduce():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_overlap_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    for _, ok, quiet, nchunks in res:
+        assert ok and quiet and nchunks == 3

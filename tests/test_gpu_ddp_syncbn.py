@@ -64,6 +64,8 @@ def _worker(rank, world, port, mode, out_path):
             from amb200.optim import FusedAdamW
             opt = FusedAdamW([p for p in net.parameters() if p.requires_grad], lr=1e-4, weight_decay=0.0)
             opt.zero_grad()
+            opt.enable_overlap(3)   # pieces of the flat buffer are all-reduced while backward is still running
+            opt.begin_overlap()
         x0, t, noise, kw = _batch(rank * per, (rank + 1) * per, dev)
         loss = diff.training_losses(net, x0, t, model_kwargs=kw, noise=noise)["loss"].mean()
         loss.backward()

@@ -319,6 +319,28 @@ def test_mha_tc_vs_fp64(B, S):
         assert (o1.view(B * S, -1) - out).abs().max() < 5e-5
 
 
+@pytest.mark.parametrize("B,S,q0", [(3, 326, 130), (2, 212, 16), (2, 384, 255), (1, 130, 129), (33, 326, 130)])
+def test_mha_tc_query_row_window(B, S, q0):
+    """am_mha_tc_fwd_rows (query rows [q0, S) only, compact output) == the same rows of the full kernel, bit for bit."""
+    g = torch.Generator().manual_seed(S + q0)
+    H, hd = 8, 64
+    qkv = torch.randn(B * S, 3 * H * hd, generator=g)
+    pad = torch.zeros(B, S, dtype=torch.bool)
+    pad[0, S - 37:] = True
+    pad[-1, 5:9] = True
+    pad_d = _cuda(pad.to(torch.uint8))
+    qkv2 = ops.split_bf16(_cuda(qkv), B * S, 3 * H * hd)
+    full32 = torch.empty(B * S, H * hd, device=DEV)
+    full2 = torch.zeros(B * S, 2 * H * hd, dtype=torch.bfloat16, device=DEV)
+    ops.mha_tc_fwd(qkv2, full32, full2, pad_d, B, S, H, hd, hd ** -0.5)
+    So = S - q0
+    win32 = torch.full((B * So, H * hd), float("nan"), device=DEV)
+    win2 = torch.full((B * So, 2 * H * hd), float("nan"), dtype=torch.bfloat16, device=DEV)
+    ops.mha_tc_fwd(qkv2, win32, win2, pad_d, B, S, H, hd, hd ** -0.5, q_row0=q0)
+    assert torch.equal(win32.view(B, So, -1), full32.view(B, S, -1)[:, q0:])
+    assert torch.equal(win2.view(B, So, -1), full2.view(B, S, -1)[:, q0:])
+
+
 # ------------------------------------------------------------------ network parity vs reference-generated goldens
 @pytest.mark.parametrize("N", [1024, 8192])
 def test_cmdm_forward_matches_reference(golden_dir, cmdm_models, N):

@@ -25,7 +25,7 @@ for t in range(3):
     print(t, d[8 + t] - t0, d[16 + t] - t0, d[32 + t] - t0, d[40 + t] - t0, d[48 + t] - t0, d[24 + t] - t0, d[56 + t] - t0)
 
 if os.environ.get("AMB200_ATTN_PIPE", "1") != "0":
-    print("tile 1, MMA warp: p_ready[chunk] seen:", [d[64 + c] - t0 for c in range(12)])
-    print("tile 1, PV(key tile) issued:", [d[80 + j] - t0 for j in range(3)], " QK(t+1, kt) issued:", [d[88 + k] - t0 if d[88 + k] else None for k in range(3)])
-    print("tile 1, block j finished by its softmax group:", [d[96 + j] - t0 for j in range(6)])
-    print("epilogue (O read, stores done) group 0 / group 1 per tile:", [((d[104 + 4 * t] - t0, d[106 + 4 * t] - t0), (d[105 + 4 * t] - t0, d[107 + 4 * t] - t0)) for t in range(3)])
+    print("tile 1, MMA warp: p_ready[chunk] seen:", [d[64 + c] - t0 for c in range(12) if d[64 + c]])
+    print("tile 1, QK(t+1, kt) issued:", [d[88 + k] - t0 if d[88 + k] else None for k in range(3)])
+    print("tile 1, block j finished by its softmax group:", [d[96 + c] - t0 for c in range(6) if d[96 + c]])
+    print("epilogue (O read, staged) group 0 / group 1 per tile:", [((d[104 + 4 * t] - t0, d[106 + 4 * t] - t0), (d[105 + 4 * t] - t0, d[107 + 4 * t] - t0)) for t in range(3)])

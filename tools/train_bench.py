@@ -35,6 +35,9 @@ net.train()
 if mode == "native":
     from amb200.optim import FusedAdamW
     opt = FusedAdamW([p for p in net.parameters() if p.requires_grad], lr=1e-4, weight_decay=0.0)
+    overlap = world > 1 and os.environ.get("AMB200_GRAD_OVERLAP", "1") != "0"
+    if overlap:
+        opt.enable_overlap(3)
 else:
     opt = torch.optim.AdamW([p for p in net.parameters() if p.requires_grad], lr=1e-4, weight_decay=0.0)
 txt = synth.text_features(B, seed=rank).to(dev)
@@ -50,6 +53,8 @@ for it in range(steps + 2):
     t = uniform_sampling(B, dev, diff.num_timesteps)
     terms = diff.training_losses(net, x0, t, model_kwargs=kw)
     loss = terms["loss"].mean()
+    if mode == "native" and overlap:
+        opt.begin_overlap()
     loss.backward()
     if mode == "native":
         opt.all_reduce_grads()
