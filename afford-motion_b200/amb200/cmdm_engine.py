@@ -239,7 +239,8 @@ class CMDMEngine:
         cur, curS = X0.view(M, D), X0S
         ffp = ops.pad32(self.ff)
         fuse_ln = self.fuse_ln and D == 512 and ffp % 64 == 0
-        compact = False
+        compact = rs_written = False
+        will_compact = self.last_compact and self.attn == "tc" and S <= 384 and hd == 64 and not fuse_ln
         for i in range(self.nlayers):
             p = f"l{i}."
             last = i == self.nlayers - 1
@@ -247,14 +248,15 @@ class CMDMEngine:
             # The last layer's output is only read at the motion tokens (models/cmdm.py:183-186 slices x[non_motion_token:]) and
             # every row is independent after the attention: its attention runs on the query rows [2+G, S) only and writes them
             # compactly, and out_proj / LayerNorm / feed-forward / motion_layer run on B*T rows instead of B*S (60 % at T=196, G=128).
-            compact = last and self.last_compact and self.attn == "tc" and S <= 384 and hd == 64 and not fuse_ln
+            compact = last and will_compact
             Mr = B * T if compact else M     # rows from the attention output onwards
             resS = curS
             if self.attn == "tc" and S <= 384 and hd == 64:
                 ops.linear_tc(curS, w[p + "in_w2"], M, 3 * D, D, y2=ws["QKVS"], bias=w[p + "in_b"], Np2=3 * D)
                 ops.mha_tc_fwd(ws["QKVS"], None, ws["ATTS"], cond.key_pad, B, S, H, hd, 1.0 / math.sqrt(hd), q_row0=2 + G if compact else 0)
                 if compact:   # the residual stream of the same rows
-                    ws["RS"].view(B, T, 2 * D).copy_(curS.view(B, S, 2 * D)[:, 2 + G:, :])
+                    if not rs_written:   # a single-layer trunk: no LayerNorm in front wrote it
+                        ws["RS"].view(B, T, 2 * D).copy_(curS.view(B, S, 2 * D)[:, 2 + G:, :])
                     resS = ws["RS"]
             # residual streams travel as the bf16 (hi|lo) pairs the LayerNorm / adapter epilogues already write for the next
             # GEMM's A operand (x = hi + lo, 16 significant bits): no fp32 copy of the activations is written at all
@@ -269,7 +271,12 @@ class CMDMEngine:
                 ops.layernorm(ws["TMP"], w[p + "n1g"], w[p + "n1b"], None, Mr, D, eps=w[p + "eps1"], y2=ws["Y1S"])
                 ops.linear_tc(ws["Y1S"], w[p + "w12"], Mr, self.ff, D, y2=ws["FFS"], bias=w[p + "b1"], act="gelu", Np2=ffp)
                 ops.linear_tc(ws["FFS"], w[p + "w22"], Mr, D, ffp, y=ws["TMP"], bias=w[p + "b2"], residual_split=ws["Y1S"])
-                ops.layernorm(ws["TMP"], w[p + "n2g"], w[p + "n2b"], None, Mr, D, eps=w[p + "eps2"], y2=nxtS)
+                if will_compact and i == self.nlayers - 2:
+                    # the LayerNorm in front of the last layer also writes the motion rows compactly: the last layer's residual stream
+                    ops.layernorm(ws["TMP"], w[p + "n2g"], w[p + "n2b"], None, Mr, D, eps=w[p + "eps2"], y2=nxtS, y2_win=ws["RS"], seg=S, seg_q0=2 + G)
+                    rs_written = True
+                else:
+                    ops.layernorm(ws["TMP"], w[p + "n2g"], w[p + "n2b"], None, Mr, D, eps=w[p + "eps2"], y2=nxtS)
             cur, curS = nxt, nxtS
         if out is None:
             out = torch.empty(B, T, Dm, device=x.device)

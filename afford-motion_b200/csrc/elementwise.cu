@@ -81,8 +81,12 @@ __global__ void sampler_update_kernel(const float* __restrict__ x0_hat, const fl
     }
     int64_t nblk = (per_sample + 3) / 4;
     int64_t total = nblk * B;
+    // index arithmetic in 32 bits whenever the job allows it (64-bit integer division is ~100 instructions; the split output below
+    // used to take five of them per thread and, not the Philox / Box-Muller math, paced this kernel)
+    const bool small = total < (int64_t)0x7fffffff / 4;
+    const int frames = nx.xs2 ? (int)(per_sample / nx.D) : 0;
     for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
-        int b = (int)(g / nblk);
+        int b = small ? (int)((uint32_t)g / (uint32_t)nblk) : (int)(g / nblk);
         int64_t blk = g - (int64_t)b * nblk;
         int tb = t[b * t_stride];
         StepCoef k;
@@ -109,11 +113,14 @@ __global__ void sampler_update_kernel(const float* __restrict__ x0_hat, const fl
             *reinterpret_cast<float4*>(x_prev + base) = o;
             if (nx.xs2) {
                 const float ov[4] = {o.x, o.y, o.z, o.w};
+                // frame / column of the first element by one division, then walk (a frame boundary may fall inside the 4 elements)
+                int64_t fr = small ? (int64_t)((uint32_t)(blk * 4) / (uint32_t)nx.D) : (blk * 4) / nx.D;
+                int col = (int)(blk * 4 - fr * nx.D);
+                __nv_bfloat16* row = nx.xs2 + ((int64_t)b * frames + fr) * 2 * nx.Kx;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const int64_t e = blk * 4 + i, fr = e / nx.D;
-                    __nv_bfloat16* row = nx.xs2 + ((int64_t)b * (per_sample / nx.D) + fr) * 2 * nx.Kx + (e - fr * nx.D);
-                    put_split(row, row + nx.Kx, ov[i]);
+                    put_split(row + col, row + nx.Kx + col, ov[i]);
+                    if (++col == nx.D) { col = 0; row += 2 * nx.Kx; }
                 }
             }
         } else {
@@ -122,7 +129,7 @@ __global__ void sampler_update_kernel(const float* __restrict__ x0_hat, const fl
                 x_prev[base + i] = o;
                 if (nx.xs2) {
                     const int64_t el = blk * 4 + i, fr = el / nx.D;
-                    __nv_bfloat16* row = nx.xs2 + ((int64_t)b * (per_sample / nx.D) + fr) * 2 * nx.Kx + (el - fr * nx.D);
+                    __nv_bfloat16* row = nx.xs2 + ((int64_t)b * frames + fr) * 2 * nx.Kx + (el - fr * nx.D);
                     put_split(row, row + nx.Kx, o);
                 }
             }

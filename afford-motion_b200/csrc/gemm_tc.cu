@@ -1053,20 +1053,20 @@ gemm_tc_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 template <int BN_, int NST, int ACT, int MODE, int BK>
 __global__ void __launch_bounds__(TCP_THREADS, 1)
 gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   const __grid_constant__ CUtensorMap tmBq, const __grid_constant__ CUtensorMap tmY,
-                   const __grid_constant__ CUtensorMap tmR, TcParams p, int n_tiles, int wide_items, int total_items) {
+                   const __grid_constant__ CUtensorMap tmBq, const __grid_constant__ CUtensorMap tmBo, const __grid_constant__ CUtensorMap tmY,
+                   const __grid_constant__ CUtensorMap tmR, TcParams p, int n_tiles, int wide_items, int total_items, int tail_shift) {
     // Work items: [0, wide_items) are 256 x BN_ pair tiles (m-pair = idx / n_tiles, n-tile = idx % n_tiles); items beyond are the
-    // REMAINING pair tiles cut into two BN_/2-wide halves each.  M*N / (148 SMs x tile) is rarely an integer (2.2 for the
-    // N = 512 / 1024 trunk GEMMs): instead of a third full round on a fifth of the SMs, the last partial round runs as
-    // half-width tiles spread over twice as many CTA pairs (tmBq: W box of BN_/4 rows per CTA).
-    auto decode = [&](int idx, int& mp, int& n0, bool& narrow) {
-        if (idx < wide_items) { mp = idx / n_tiles; n0 = (idx % n_tiles) * BN_; narrow = false; }
+    // REMAINING pair tiles cut into 2^tail_shift pieces of BN_ >> tail_shift columns each.  M*N / (148 SMs x tile) is rarely an
+    // integer (1.1 for the N = 512 trunk GEMMs, 2.2 for N = 1024): instead of another full round on a fraction of the SMs, the last
+    // partial round runs as half- or quarter-width tiles spread over 2x / 4x as many CTA pairs (tmBq / tmBo: W boxes of BN_/4 / BN_/8
+    // rows per CTA); the host picks the shift with the smaller estimated makespan.
+    auto decode = [&](int idx, int& mp, int& n0, int& sh) {
+        if (idx < wide_items) { mp = idx / n_tiles; n0 = (idx % n_tiles) * BN_; sh = 0; }
         else {
-            const int u = idx - wide_items, w = wide_items + (u >> 1);
-            mp = w / n_tiles; n0 = (w % n_tiles) * BN_ + (u & 1) * (BN_ / 2); narrow = true;
+            const int u = idx - wide_items, w = wide_items + (u >> tail_shift);
+            mp = w / n_tiles; n0 = (w % n_tiles) * BN_ + (u & ((1 << tail_shift) - 1)) * (BN_ >> tail_shift); sh = tail_shift;
         }
     };
-    constexpr uint32_t IDESC_N = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((BN_ / 2) >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
     // BK = 32: 64-byte operand rows (SWIZZLE_64B); BK = 64: 128-byte rows (SWIZZLE_128B)
     constexpr int A_SUB = BM * BK * 2;            // this CTA's 128 rows of A (hi or lo)
     constexpr int B_SUB = (BN_ / 2) * BK * 2;     // this CTA's half of the W tile (hi or lo)
@@ -1126,12 +1126,12 @@ gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             constexpr bool FAST = decltype(fc)::value;
             uint32_t kbc = 0;
             for (int tile = cluster_id; tile < total_items; tile += num_clusters) {
-                int mp, n0; bool narrow;
-                decode(tile, mp, n0, narrow);
+                int mp, n0, sh;
+                decode(tile, mp, n0, sh);
                 const int m0 = (mp * 2 + (int)cta_rank) * BM;
-                const int nh = n0 + (int)cta_rank * (narrow ? BN_ / 4 : BN_ / 2);
-                const CUtensorMap* tmW = narrow ? &tmBq : &tmB;
-                const uint32_t stage_tx = FAST ? (uint32_t)(A_SUB + (narrow ? B_SUB / 2 : B_SUB)) : (uint32_t)(2 * A_SUB + (narrow ? B_SUB : 2 * B_SUB));
+                const int nh = n0 + (int)cta_rank * (BN_ >> (sh + 1));
+                const CUtensorMap* tmW = sh == 0 ? &tmB : (sh == 1 ? &tmBq : &tmBo);
+                const uint32_t stage_tx = FAST ? (uint32_t)(A_SUB + (B_SUB >> sh)) : (uint32_t)(2 * A_SUB + 2 * (B_SUB >> sh));
                 for (int kb = 0; kb < nkb; ++kb, ++kbc) {
                     const int s = kbc % NST;
                     mbar_wait(&empty[s], ((kbc / NST) & 1) ^ 1);   // released in both CTAs by the leader's commit multicast
@@ -1163,7 +1163,8 @@ gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             int it = 0;
             for (int tile = cluster_id; tile < total_items; tile += num_clusters, ++it) {
                 const int ab = it & 1;
-                const uint32_t idesc = tile < wide_items ? IDESC_P : IDESC_N;
+                const uint32_t idesc = tile < wide_items ? IDESC_P
+                    : ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((BN_ >> tail_shift) >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24));
                 mbar_wait(&tmem_empty[ab], (((it >> 1) & 1) ^ 1));
                 tc_fence_after();
                 const uint32_t d = tmem_base + (uint32_t)(ab * BN_);
@@ -1203,13 +1204,17 @@ gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         uint32_t epi_phases = 0;
         for (int tile = cluster_id; tile < total_items; tile += num_clusters, ++it) {
             const int ab = it & 1;
-            int mp, n0; bool narrow;
-            decode(tile, mp, n0, narrow);
+            int mp, n0, sh;
+            decode(tile, mp, n0, sh);
             const int m0 = (mp * 2 + (int)cta_rank) * BM;
             uint32_t lempty;  // the leader's tmem_empty[ab]
             asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(lempty) : "r"(smem_u32(&tmem_empty[ab])), "r"(0u));
             if (MODE == 4) {
-                if (narrow)
+                if (sh == 2)
+                    epilogue_tile_tma_f32<ACT, BN_ / 4>(p, &tmY, &tmR, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane,
+                                                        smem_u32(stage_buf + warp * (32 * 32)), smem_u32(epi_bars + warp * 2), epi_phases,
+                                                        &tmem_full[ab], (uint32_t)((it >> 1) & 1));
+                else if (sh == 1)
                     epilogue_tile_tma_f32<ACT, BN_ / 2>(p, &tmY, &tmR, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane,
                                                         smem_u32(stage_buf + warp * (32 * 32)), smem_u32(epi_bars + warp * 2), epi_phases,
                                                         &tmem_full[ab], (uint32_t)((it >> 1) & 1));
@@ -1220,7 +1225,8 @@ gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             } else {
                 mbar_wait(&tmem_full[ab], (it >> 1) & 1);
                 tc_fence_after();
-                if (MODE == 3 && narrow) epilogue_tile_tma<ACT, BN_ / 2>(p, &tmY, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane, smem_u32(stage_buf + warp * (32 * 32)));
+                if (MODE == 3 && sh == 2) epilogue_tile_tma<ACT, BN_ / 4>(p, &tmY, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane, smem_u32(stage_buf + warp * (32 * 32)));
+                else if (MODE == 3 && sh == 1) epilogue_tile_tma<ACT, BN_ / 2>(p, &tmY, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane, smem_u32(stage_buf + warp * (32 * 32)));
                 else if (MODE == 3) epilogue_tile_tma<ACT, BN_>(p, &tmY, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane, smem_u32(stage_buf + warp * (32 * 32)));
                 else if (MODE == 0) epilogue_tile_coalesced<ACT, BN_>(p, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane, stage_buf + warp * (32 * 32));
                 else if (MODE == 5) epilogue_tile_fast_mapped<ACT, BN_>(p, tmem_base + (uint32_t)(ab * BN_), m0, n0, q, half, lane, smem_u32(stage_buf + warp * (32 * 32)));
@@ -1314,6 +1320,30 @@ extern "C" int am_split_bf16(const float* X, int ldx, void* X2, int Kp, int M, i
     return AM_OK;
 }
 
+// Tail plan of the CTA-pair kernel: `pairs` 256 x 256 tiles on `clusters` CTA pairs.  Full rounds run as whole tiles; the remaining
+// `rem` tiles are cut into 2^shift column pieces each so that the last round is short.  Estimated makespan in tile-times: a half-width
+// piece costs 0.54, a quarter-width piece 0.30 (A is re-read per piece and the fixed per-item cost does not shrink); shift 0 = no cut.
+// AMB200_TC_TAIL=half|quarter|none forces one plan (A/B timing).
+static void tc_tail_plan(int pairs, int clusters, int& wide, int& shift) {
+    static int force = -2;
+    if (force == -2) {
+        const char* e = getenv("AMB200_TC_TAIL");
+        force = !e ? -1 : (!strcmp(e, "none") ? 0 : (!strcmp(e, "half") ? 1 : (!strcmp(e, "quarter") ? 2 : -1)));
+    }
+    const int full = (pairs / clusters) * clusters, rem = pairs - full;
+    if (rem == 0 || force == 0) { wide = pairs; shift = 1; return; }
+    const double c[3] = {1.0, 0.54, 0.30};
+    int best = 0;
+    double best_cost = 1e30;
+    for (int sh = 0; sh <= 2; ++sh) {
+        if (force > 0 && sh != force) continue;
+        const int items = rem << sh;
+        const double cost = (double)((items + clusters - 1) / clusters) * c[sh];
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = sh; }
+    }
+    if (best == 0) { wide = pairs; shift = 1; } else { wide = full; shift = best; }
+}
+
 extern "C" int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp, const float* bias, int act, const float* residual, int ldr,
                             int res_mod, float* Y, int ldy, int yin_g, int yout_g, int y_off, void* Y2, int Np2, am_stream_t stream) {
     AM_REQUIRE(A2 && W2 && (Y || Y2), AM_EINVAL, "am_linear_tc: null pointer");
@@ -1380,9 +1410,10 @@ extern "C" int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp
             AM_REQUIRE(make_map(&tmBh64, W2, (uint64_t)N, (uint64_t)2 * Kp, 64, bn / 2), AM_ELAUNCH, "am_linear_tc: cuTensorMapEncodeTiled(W half, BK=64) failed");
         }
         // mixed-width tail (CTA-pair kernel, 256-wide tiles): W quarter-tile map for the half-width items
-        CUtensorMap tmBq = tmB;
+        CUtensorMap tmBq = tmB, tmBo = tmB;
         const bool mixed_ok = use_2sm && bn == 256 && g_tc_mixed != 0;
         if (mixed_ok) AM_REQUIRE(make_map(&tmBq, W2, (uint64_t)N, (uint64_t)2 * Kp, bk2, bn / 4), AM_ELAUNCH, "am_linear_tc: cuTensorMapEncodeTiled(W quarter) failed");
+        if (mixed_ok) AM_REQUIRE(make_map(&tmBo, W2, (uint64_t)N, (uint64_t)2 * Kp, bk2, bn / 8), AM_ELAUNCH, "am_linear_tc: cuTensorMapEncodeTiled(W eighth) failed");
         if (use_cluster || use_2sm) AM_REQUIRE(make_map(&tmBh, W2, (uint64_t)N, (uint64_t)2 * Kp, 32, bn / 2), AM_ELAUNCH, "am_linear_tc: cuTensorMapEncodeTiled(W half) failed");
 #define AM_TC2_LAUNCH(BN_, NST2_, ACT_, MODE_, BK_)                                                                             \
     do {                                                                                                                        \
@@ -1397,10 +1428,11 @@ extern "C" int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp
             attr3_ = true;                                                                                                      \
         }                                                                                                                       \
         const bool mixed_ = mixed_ok && BN_ == 256 && (MODE_ == 3 || MODE_ == 4);                                               \
-        const int wide_ = mixed_ ? (pairs / (grid_cl / 2)) * (grid_cl / 2) : pairs;                                              \
-        const int items_ = wide_ + 2 * (pairs - wide_);                                                                         \
+        int wide_ = pairs, shift_ = 1;                                                                                          \
+        if (mixed_) tc_tail_plan(pairs, grid_cl / 2, wide_, shift_);                                                            \
+        const int items_ = wide_ + ((pairs - wide_) << shift_);                                                                 \
         if (am_launch(gemm_tc_2sm_kernel<BN_, NST2_, ACT_, MODE_, BK_>, dim3(grid_cl), dim3(TCP_THREADS), smem2_, st, 2,       \
-                      (bk2 == 64 ? tmA64 : tmA), (bk2 == 64 ? tmBh64 : tmBh), tmBq, tmY, tmR, p, nt, wide_, items_) != cudaSuccess) { \
+                      (bk2 == 64 ? tmA64 : tmA), (bk2 == 64 ? tmBh64 : tmBh), tmBq, tmBo, tmY, tmR, p, nt, wide_, items_, shift_) != cudaSuccess) { \
             am_set_error_("am_linear_tc: CTA-pair launch failed");                                                              \
             return AM_ELAUNCH;                                                                                                  \
         }                                                                                                                       \

@@ -61,12 +61,19 @@ template <int NV>
 __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ R, int ldr,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             float* __restrict__ Y, int ldy, int M, int D, float eps,
-                                                            __nv_bfloat16* __restrict__ Y2, int Np2) {
+                                                            __nv_bfloat16* __restrict__ Y2, int Np2,
+                                                            __nv_bfloat16* __restrict__ Y2w, int seg, int seg_q0) {
     pdl_launch_dependents();
     pdl_wait();
     int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= M) return;
     int lane = threadIdx.x & 31;
+    // optional second, COMPACT copy of the rows [seg_q0, seg) of every `seg`-row segment (am_layernorm_win)
+    __nv_bfloat16* w2 = nullptr;
+    if (Y2w) {
+        const int sg = row / seg, i = row - sg * seg;
+        if (i >= seg_q0) w2 = Y2w + ((int64_t)sg * (seg - seg_q0) + (i - seg_q0)) * 2 * Np2;
+    }
     const float4* x4 = reinterpret_cast<const float4*>(X + (int64_t)row * ldx);
     const float4* r4 = R ? reinterpret_cast<const float4*>(R + (int64_t)row * ldr) : nullptr;
     float4 v[NV];
@@ -103,14 +110,22 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restr
             uint2* hi = reinterpret_cast<uint2*>(Y2 + (int64_t)row * 2 * Np2) + c;
             hi[0] = make_uint2(u01, u23);
             hi[Np2 / 4] = make_uint2(*reinterpret_cast<uint32_t*>(&l01), *reinterpret_cast<uint32_t*>(&l23));
+            if (w2) {
+                uint2* wh = reinterpret_cast<uint2*>(w2) + c;
+                wh[0] = make_uint2(u01, u23);
+                wh[Np2 / 4] = make_uint2(*reinterpret_cast<uint32_t*>(&l01), *reinterpret_cast<uint32_t*>(&l23));
+            }
         }
     }
 }
 
 }  // namespace
 
-extern "C" int am_layernorm(const float* X, int ldx, const float* R, int ldr, const float* gamma, const float* beta, float* Y, int ldy,
-                            int M, int D, float eps, void* Y2, int Np2, am_stream_t stream) {
+extern "C" int am_layernorm_win(const float* X, int ldx, const float* R, int ldr, const float* gamma, const float* beta, float* Y, int ldy,
+                                int M, int D, float eps, void* Y2, int Np2, void* Y2w, int seg, int seg_q0, am_stream_t stream) {
+    AM_REQUIRE(!Y2w || (Y2 && seg > 0 && seg_q0 >= 0 && seg_q0 < seg && M % seg == 0 && (reinterpret_cast<uintptr_t>(Y2w) & 15u) == 0), AM_EINVAL,
+               "am_layernorm_win: the window copy needs Y2, 0 <= seg_q0 < seg, M % seg == 0 and a 16-byte aligned Y2w");
+    __nv_bfloat16* y2w = reinterpret_cast<__nv_bfloat16*>(Y2w);
     AM_REQUIRE(X && gamma && beta && (Y || Y2) && M > 0 && D > 0 && D <= 1024, AM_EINVAL, "am_layernorm: bad args (D <= 1024)");
     AM_REQUIRE(ldx >= D && (!Y || ldy >= D) && (!R || ldr >= D), AM_EINVAL, "am_layernorm: bad strides");
     AM_REQUIRE(!Y2 || (Np2 >= D && Np2 % 32 == 0 && Np2 <= 1024), AM_EINVAL, "am_layernorm: bad Np2");
@@ -121,19 +136,25 @@ extern "C" int am_layernorm(const float* X, int ldx, const float* R, int ldr, co
                      (!Y || (a16(Y) && ldy % 4 == 0)) && (!Y2 || (a16(Y2) && Np2 == D));
     if (vec) {
         switch (D / 128) {
-            case 1: am_launch(layernorm_vec_kernel<1>, dim3(grid), dim3(256), 0, as_stream(stream), 1, X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2); break;
-            case 2: am_launch(layernorm_vec_kernel<2>, dim3(grid), dim3(256), 0, as_stream(stream), 1, X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2); break;
-            case 4: am_launch(layernorm_vec_kernel<4>, dim3(grid), dim3(256), 0, as_stream(stream), 1, X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2); break;
-            case 8: am_launch(layernorm_vec_kernel<8>, dim3(grid), dim3(256), 0, as_stream(stream), 1, X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2); break;
+            case 1: am_launch(layernorm_vec_kernel<1>, dim3(grid), dim3(256), 0, as_stream(stream), 1, X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2, y2w, seg, seg_q0); break;
+            case 2: am_launch(layernorm_vec_kernel<2>, dim3(grid), dim3(256), 0, as_stream(stream), 1, X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2, y2w, seg, seg_q0); break;
+            case 4: am_launch(layernorm_vec_kernel<4>, dim3(grid), dim3(256), 0, as_stream(stream), 1, X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2, y2w, seg, seg_q0); break;
+            case 8: am_launch(layernorm_vec_kernel<8>, dim3(grid), dim3(256), 0, as_stream(stream), 1, X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2, y2w, seg, seg_q0); break;
             default: goto scalar_path;
         }
         AM_LAUNCH_CHECK("layernorm");
         return AM_OK;
     }
 scalar_path:
+    AM_REQUIRE(!Y2w, AM_EINVAL, "am_layernorm_win: the window copy is implemented for the vectorised path only (D % 128 == 0, aligned)");
     if (D <= 256) am_launch(layernorm_kernel<8>, dim3(grid), dim3(256), 0, as_stream(stream), 1, X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2);
     else if (D <= 512) am_launch(layernorm_kernel<16>, dim3(grid), dim3(256), 0, as_stream(stream), 1, X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2);
     else am_launch(layernorm_kernel<32>, dim3(grid), dim3(256), 0, as_stream(stream), 1, X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2);
     AM_LAUNCH_CHECK("layernorm");
     return AM_OK;
+}
+
+extern "C" int am_layernorm(const float* X, int ldx, const float* R, int ldr, const float* gamma, const float* beta, float* Y, int ldy,
+                            int M, int D, float eps, void* Y2, int Np2, am_stream_t stream) {
+    return am_layernorm_win(X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, Y2, Np2, nullptr, 0, 0, stream);
 }

@@ -124,6 +124,11 @@ int am_linear_f32_batched(const float* X, int ldx, const float* W, int ldw, floa
 /* Y = LayerNorm(X (+ R)) * gamma + beta, eps inside sqrt (torch.nn.LayerNorm); rows of length D <= 1024 */
 int am_layernorm(const float* X, int ldx, const float* R, int ldr, const float* gamma, const float* beta,
                  float* Y, int ldy, int M, int D, float eps, void* Y2, int Np2, am_stream_t stream);
+/* Same, plus an optional second COMPACT copy of the bf16 (hi|lo) output: rows [seg_q0, seg) of every `seg`-row segment (M % seg == 0)
+ * go to Y2w [(M / seg) * (seg - seg_q0), 2*Np2] as well.  The LayerNorm in front of the last CMDM encoder layer writes the residual
+ * stream of the motion tokens this way (models/cmdm.py:183-186 only reads those rows of the last layer). */
+int am_layernorm_win(const float* X, int ldx, const float* R, int ldr, const float* gamma, const float* beta, float* Y, int ldy,
+                     int M, int D, float eps, void* Y2, int Np2, void* Y2w, int seg, int seg_q0, am_stream_t stream);
 /* (Y2 != NULL additionally writes the bf16 (hi|lo) split [M, 2*Np2] that feeds am_linear_tc; Y may then be NULL) */
 
 /* Multi-head self attention core of torch.nn.TransformerEncoderLayer (models/cmdm.py:66-77,167):

@@ -26,10 +26,10 @@ reps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 for _ in range(reps):   # exactly the per-layer sequence of amb200.cmdm_engine._forward_tc
     ops.linear_tc(xs, wins, M, 3 * D, D, y2=qkvs, bias=bias3, Np2=3 * D)                 # in_proj -> bf16 (hi|lo) QKV
     ops.mha_tc_fwd(qkvs, None, atts, pad, B, S, H, 64, 0.125)                           # tcgen05 attention
-    ops.linear_tc(atts, wouts, M, D, D, y=tmp, bias=bias1, residual=x)                  # out_proj + residual
-    ops.layernorm(tmp, gam, bet, y1, M, D, y2=y1s)                                      # LN1
+    ops.linear_tc(atts, wouts, M, D, D, y=tmp, bias=bias1, residual_split=xs)           # out_proj + residual (bf16 hi|lo stream)
+    ops.layernorm(tmp, gam, bet, None, M, D, y2=y1s)                                    # LN1 -> bf16 (hi|lo) only
     ops.linear_tc(y1s, w1s, M, FF, D, y2=ffs, bias=biasf, act="gelu", Np2=FF)           # FFN1 + GELU (split out only)
-    ops.linear_tc(ffs, w2s, M, D, FF, y=tmp, bias=bias1, residual=y1)                   # FFN2 + residual
-    ops.layernorm(tmp, gam, bet, y1, M, D, y2=y1s)                                      # LN2
+    ops.linear_tc(ffs, w2s, M, D, FF, y=tmp, bias=bias1, residual_split=y1s)            # FFN2 + residual
+    ops.layernorm(tmp, gam, bet, None, M, D, y2=xs)                                     # LN2
 torch.cuda.synchronize()
 print("done")
