@@ -46,6 +46,8 @@ class CMDMEngine:
         # measured 44.3 / 58.9 us against 34.1 / 42.8 us for GEMM + LayerNorm (profiles/r2_gemm_ln_fused_ab.txt) — its row-per-lane
         # epilogue is bound by uncoalesced residual / output accesses; parity-tested, kept for the next round
         self.fuse_ln = os.environ.get("AMB200_LN_FUSE", "0") == "1"
+        # LayerNorms overlapped with the GEMM in front of them through row-block flags (am_linear_tc_set_rowflags / am_layernorm_flags)
+        self.ln_overlap = os.environ.get("AMB200_LN_OVERLAP", "0") == "1"
         # last encoder layer on the motion rows only (am_mha_tc_fwd_rows); needs the pipelined attention kernel
         self.last_compact = os.environ.get("AMB200_LAST_COMPACT", "1") == "1" and os.environ.get("AMB200_ATTN_PIPE", "1") != "0"
         assert self.attn in ("tc", "simt")
@@ -156,7 +158,7 @@ class CMDMEngine:
                 bf = lambda r, c: torch.zeros(r, c, dtype=torch.bfloat16, device=dev)
                 ws.update({"X0S": bf(M, 2 * D), "XSa": bf(M, 2 * D), "XSb": bf(M, 2 * D), "ATTS": bf(M, 2 * D), "Y1S": bf(M, 2 * D),
                            "FFS": bf(M, 2 * ops.pad32(ff)), "xS": bf(B * T, 2 * ops.pad32(self.m.motion_dim)), "QKVS": bf(M, 6 * D),
-                           "RS": bf(B * T, 2 * D)})
+                           "RS": bf(B * T, 2 * D), "FLAGS": torch.zeros((M + 127) // 128 + 1, dtype=torch.int32, device=dev)})
             self._ws[key] = ws
         return ws
 
@@ -240,6 +242,7 @@ class CMDMEngine:
         ffp = ops.pad32(self.ff)
         fuse_ln = self.fuse_ln and D == 512 and ffp % 64 == 0
         compact = rs_written = False
+        ovl = self.ln_overlap and D % 128 == 0 and D % 256 == 0 and not fuse_ln
         will_compact = self.last_compact and self.attn == "tc" and S <= 384 and hd == 64 and not fuse_ln
         for i in range(self.nlayers):
             p = f"l{i}."
@@ -267,6 +270,17 @@ class CMDMEngine:
                 ops.linear_tc(ws["Y1S"], w[p + "w12"], M, self.ff, D, y2=ws["FFS"], bias=w[p + "b1"], act="gelu", Np2=ffp)
                 ops.linear_ln_tc(ws["FFS"], w[p + "w22"], M, D, ffp, w[p + "b2"], ws["Y1S"], w[p + "n2g"], w[p + "n2b"], w[p + "eps2"], nxtS)
             else:
+                win = dict(y2_win=ws["RS"], seg=S, seg_q0=2 + G) if (will_compact and i == self.nlayers - 2) else {}
+                if ovl and (Mr + 127) // 128 >= 7:   # (the CTA-pair GEMM needs >= 16 pair tiles)
+                    # each LayerNorm starts on the 128-row blocks its GEMM has finished while the GEMM's tail round is still running
+                    ops.linear_tc(ws["ATTS"], w[p + "out_w2"], Mr, D, D, y=ws["TMP"], bias=w[p + "out_b"], residual_split=resS, rowflags=ws["FLAGS"])
+                    ops.layernorm_flags(ws["TMP"], w[p + "n1g"], w[p + "n1b"], Mr, D, ws["Y1S"], ws["FLAGS"], 4 * D, eps=w[p + "eps1"])
+                    ops.linear_tc(ws["Y1S"], w[p + "w12"], Mr, self.ff, D, y2=ws["FFS"], bias=w[p + "b1"], act="gelu", Np2=ffp)
+                    ops.linear_tc(ws["FFS"], w[p + "w22"], Mr, D, ffp, y=ws["TMP"], bias=w[p + "b2"], residual_split=ws["Y1S"], rowflags=ws["FLAGS"])
+                    ops.layernorm_flags(ws["TMP"], w[p + "n2g"], w[p + "n2b"], Mr, D, nxtS, ws["FLAGS"], 4 * D, eps=w[p + "eps2"], **win)
+                    rs_written = rs_written or bool(win)
+                    cur, curS = nxt, nxtS
+                    continue
                 ops.linear_tc(ws["ATTS"], w[p + "out_w2"], Mr, D, D, y=ws["TMP"], bias=w[p + "out_b"], residual_split=resS)
                 ops.layernorm(ws["TMP"], w[p + "n1g"], w[p + "n1b"], None, Mr, D, eps=w[p + "eps1"], y2=ws["Y1S"])
                 ops.linear_tc(ws["Y1S"], w[p + "w12"], Mr, self.ff, D, y2=ws["FFS"], bias=w[p + "b1"], act="gelu", Np2=ffp)

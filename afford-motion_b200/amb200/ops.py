@@ -118,6 +118,14 @@ def layernorm(x, gamma, beta, y, M, D, residual=None, eps=1e-5, ldx=None, ldy=No
     return y
 
 
+def layernorm_flags(x, gamma, beta, M, D, y2, flags, expect, eps=1e-5, y2_win=None, seg=0, seg_q0=0):
+    """LayerNorm overlapped with the GEMM that produces x (armed with linear_tc(..., rowflags=flags)); see am_layernorm_flags."""
+    _chk_cuda(x)
+    _l.check(_l.load().am_layernorm_flags(_ptr(x), D, _ptr(gamma), _ptr(beta), M, D, eps, _ptr(y2), pad32(D), _ptr(y2_win), int(seg), int(seg_q0),
+                                         _ptr(flags), int(expect), _stream()), "am_layernorm_flags")
+    return y2
+
+
 def mha_fwd(qkv, out, key_pad_u8, B, S, H, hd, scale, out2=None):
     _chk_cuda(qkv)
     _l.check(_l.load().am_mha_fwd(_ptr(qkv), _ptr(out), _ptr(key_pad_u8), B, S, H, hd, float(scale), _ptr(out2), _stream()), "am_mha_fwd")
@@ -268,9 +276,12 @@ def split_bf16(x, M, K, out=None, ldx=None):
 
 
 def linear_tc(a2, w2, M, N, Kp, y=None, y2=None, bias=None, act=None, residual=None, ldr=0, res_mod=0, ldy=None, ymap=(0, 0, 0), Np2=0,
-              residual_split=None):
-    """tcgen05 GEMM on split-bf16 operands (see am_linear_tc).  residual_split: bf16 (hi|lo) tensor [M, 2*N] added as hi + lo."""
+              residual_split=None, rowflags=None):
+    """tcgen05 GEMM on split-bf16 operands (see am_linear_tc).  residual_split: bf16 (hi|lo) tensor [M, 2*N] added as hi + lo.
+    rowflags: int32 [ceil(M/128)] row-block completion counters for an overlapped consumer (am_linear_tc_set_rowflags)."""
     _chk_cuda(a2, w2)
+    if rowflags is not None:
+        _l.check(_l.load().am_linear_tc_set_rowflags(_ptr(rowflags)), "am_linear_tc_set_rowflags")
     if residual_split is not None:
         assert residual is None
         residual, ldr, res_mod = residual_split, residual_split.shape[-1] // 2, -1

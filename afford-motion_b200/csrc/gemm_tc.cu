@@ -53,6 +53,8 @@ struct TcParams {
     long long* dbg;  // optional timeline buffer (tools/tc_timeline.py): CTA (0,0) records clock64() per role
     int res_split;   // MODE 4: `residual` is a bf16 (hi|lo) split tensor [M, 2*ldr] (the previous LayerNorm's only output), not fp32
     int fast;        // am_set_precision(1): single bf16 pass (A_hi W_hi^T only; the lo halves are neither loaded nor multiplied)
+    int* rowflags;   // CTA-pair kernel, MODE 4: per 128-row block, incremented as the block's output columns become globally visible
+                     // (a consumer kernel that overlaps this GEMM waits on it: am_layernorm_flags); NULL = off
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -1234,6 +1236,16 @@ gemm_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
             tc_fence_before();
             asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(lempty) : "memory");
+            if (MODE == 4 && p.rowflags) {
+                // This warp's share of the item (32 rows x half of the item's columns) is globally visible: bump the row block's
+                // counter.  The block is complete at 8 warps x N / 2 = 4 N; the consumer (am_layernorm_flags) resets it.
+                if (lane == 0) {
+                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    __threadfence();
+                    if (m0 < p.M) atomicAdd(p.rowflags + m0 / BM, (BN_ >> sh) / 2);
+                }
+            }
             if (dbg && threadIdx.x == 0 && it < 16) {
                 p.dbg[72 + it] = clock64();
                 unsigned long long ns;
@@ -1296,6 +1308,7 @@ bool make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, i
 }  // namespace
 
 static long long* g_tc_dbg = nullptr;
+static thread_local int* g_tc_next_rowflags = nullptr;   // consumed by the next am_linear_tc call of this thread (am_linear_tc_set_rowflags)
 static int g_tc_bn = 0;        // tuning hook (tools/tc_tile_sweep.py): force the tile width (128 / 256), 0 = automatic
 static int g_tc_cluster = -1;  // tuning hook: force the 2-CTA multicast kernel on (1) / off (0), -1 = AMB200_TC_CLUSTER / default
 static int g_tc_mixed = 1;     // tuning hook: 0 disables the half-width tail items of the CTA-pair kernel
@@ -1389,8 +1402,10 @@ extern "C" int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp
         CUtensorMap tmA, tmB;
         AM_REQUIRE(make_map(&tmA, A2, (uint64_t)M, (uint64_t)2 * Kp, 32, BM), AM_ELAUNCH, "am_linear_tc: cuTensorMapEncodeTiled(A) failed");
         AM_REQUIRE(make_map(&tmB, W2, (uint64_t)N, (uint64_t)2 * Kp, 32, bn), AM_ELAUNCH, "am_linear_tc: cuTensorMapEncodeTiled(W) failed");
-        TcParams p{M, N, Kp, bias, act, residual, ldr, res_mod, Y, ldy, yin_g, yout_g, y_off, reinterpret_cast<__nv_bfloat16*>(Y2), Np2, 0, g_tc_dbg, res_split, 0};
+        TcParams p{M, N, Kp, bias, act, residual, ldr, res_mod, Y, ldy, yin_g, yout_g, y_off, reinterpret_cast<__nv_bfloat16*>(Y2), Np2, 0, g_tc_dbg, res_split, 0, nullptr};
         p.fast = am_get_precision();
+        int* const want_flags = g_tc_next_rowflags;
+        g_tc_next_rowflags = nullptr;
         p.vecY = Y && (reinterpret_cast<uintptr_t>(Y) & 15u) == 0 && (ldy % 4 == 0);
         const int grid = total < AM_NUM_SMS ? total : AM_NUM_SMS;
         cudaStream_t st = as_stream(stream);
@@ -1516,6 +1531,8 @@ extern "C" int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp
             if (f32map(&tmY, Y, ldy) && (!residual || (res_split ? splitmap(&tmR) : f32map(&tmR, residual, ldr)))) mode = 4;
         }
         AM_REQUIRE(!res_split || mode == 4, AM_EINVAL, "am_linear_tc: a split residual is only supported by the TMA fp32 epilogue (plain layout, fp32 Y)");
+        AM_REQUIRE(!want_flags || (mode == 4 && use_2sm), AM_EINVAL, "am_linear_tc_set_rowflags: row-block flags need the CTA-pair kernel with the TMA fp32 epilogue");
+        p.rowflags = want_flags;
         // MODE 5: row-mapped / broadcast-residual outputs with 16-byte rows (motion_adapter)
         if (mode == 0 && (yin_g > 0 || res_mod > 0) && (N % bn) == 0 && !(act & AM_ACT_AFTER_RES) && (a15 == AM_ACT_NONE || a15 == AM_ACT_GELU) &&
             (!bias || (reinterpret_cast<uintptr_t>(bias) & 15u) == 0) &&
@@ -1550,7 +1567,7 @@ extern "C" int am_linear_tc(const void* A2, const void* W2, int M, int N, int Kp
     CUtensorMap tmA, tmB;
     AM_REQUIRE(make_map(&tmA, A2, (uint64_t)M, (uint64_t)2 * Kp, BKsel), AM_ELAUNCH, "am_linear_tc: cuTensorMapEncodeTiled(A) failed");
     AM_REQUIRE(make_map(&tmB, W2, (uint64_t)N, (uint64_t)2 * Kp, BKsel), AM_ELAUNCH, "am_linear_tc: cuTensorMapEncodeTiled(W) failed");
-    TcParams p{M, N, Kp, bias, act, residual, ldr, res_mod, Y, ldy, yin_g, yout_g, y_off, reinterpret_cast<__nv_bfloat16*>(Y2), Np2, 0, g_tc_dbg, 0};
+    TcParams p{M, N, Kp, bias, act, residual, ldr, res_mod, Y, ldy, yin_g, yout_g, y_off, reinterpret_cast<__nv_bfloat16*>(Y2), Np2, 0, g_tc_dbg, 0, 0, nullptr};
     p.vecY = Y && (reinterpret_cast<uintptr_t>(Y) & 15u) == 0 && (ldy % 4 == 0);
     dim3 grid(cdiv(N, BN), cdiv(M, BM));
     cudaStream_t st = as_stream(stream);
@@ -1613,5 +1630,14 @@ extern "C" int am_transpose_split_bf16(const float* X, int ldx, void* XT2, int M
     dim3 grid(Mp / 32, cdiv(K, 32));
     transpose_split_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>(X, ldx, reinterpret_cast<__nv_bfloat16*>(XT2), Mp, M, K);
     AM_LAUNCH_CHECK("transpose_split_bf16");
+    return AM_OK;
+}
+
+// Row-block completion flags for the NEXT am_linear_tc call of this thread (CTA-pair kernel, fp32 TMA epilogue only): flags[m / 128] is
+// incremented by (columns / 2) per epilogue warp as the block's outputs become globally visible and reaches 4 * N when the 128-row
+// block of Y is complete.  A consumer launched with programmatic dependent launch (am_layernorm_flags) starts on finished row blocks
+// while the GEMM is still computing others, and resets the counters.  flags: int32 [ceil(M / 128)], zero before the first use.
+extern "C" int am_linear_tc_set_rowflags(int* flags) {
+    g_tc_next_rowflags = flags;
     return AM_OK;
 }

@@ -129,6 +129,16 @@ int am_layernorm(const float* X, int ldx, const float* R, int ldr, const float* 
  * stream of the motion tokens this way (models/cmdm.py:183-186 only reads those rows of the last layer). */
 int am_layernorm_win(const float* X, int ldx, const float* R, int ldr, const float* gamma, const float* beta, float* Y, int ldy,
                      int M, int D, float eps, void* Y2, int Np2, void* Y2w, int seg, int seg_q0, am_stream_t stream);
+
+/* GEMM -> LayerNorm overlap (CMDM trunk: out_proj / linear2 + residual -> norm1 / norm2, models/cmdm.py:66-77).
+ * am_linear_tc_set_rowflags arms the NEXT am_linear_tc call of the calling thread (CTA-pair kernel, fp32 TMA epilogue): flags[m / 128]
+ * (int32 [ceil(M / 128)], zero before the first use) is advanced as the 128-row block's output becomes globally visible and reaches
+ * 4 * N when the block is complete.  am_layernorm_flags is launched right behind it as a programmatic dependent: one CTA per row block
+ * waits for its counter (expect = 4 * N), normalises the block while the GEMM is still computing others, and resets the counter.
+ * Outputs are bit-identical to am_layernorm_win (bf16 (hi|lo) Y2 and optional window copy Y2w). */
+int am_linear_tc_set_rowflags(int* flags);
+int am_layernorm_flags(const float* X, int ldx, const float* gamma, const float* beta, int M, int D, float eps, void* Y2, int Np2,
+                       void* Y2w, int seg, int seg_q0, int* flags, int expect, am_stream_t stream);
 /* (Y2 != NULL additionally writes the bf16 (hi|lo) split [M, 2*Np2] that feeds am_linear_tc; Y may then be NULL) */
 
 /* Multi-head self attention core of torch.nn.TransformerEncoderLayer (models/cmdm.py:66-77,167):

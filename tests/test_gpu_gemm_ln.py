@@ -32,3 +32,41 @@ def test_linear_ln_tc_vs_fp64_and_unfused(M, K):
     ops.layernorm(tmp, gam.to(DEV), bet.to(DEV), None, M, N, eps=1e-5, y2=y2u)
     un = (y2u[:, :N].float() + y2u[:, N:].float()).cpu().double()
     assert (got - un).abs().max().item() < 2e-4  # both round to bf16 pairs (16 significant bits) from slightly different fp32 values
+
+
+@pytest.mark.parametrize("M,K,seg,q0", [(10432, 512, 326, 130), (10432, 1024, 0, 0), (6272, 512, 0, 0), (978, 512, 326, 130)])
+def test_layernorm_overlapped_with_its_gemm_is_bit_identical(M, K, seg, q0):
+    """am_linear_tc_set_rowflags + am_layernorm_flags (the LayerNorm consumes 128-row blocks while the GEMM is still running, handshake
+    through per-block completion counters) == am_linear_tc followed by am_layernorm(_win), bit for bit, over repeated launches (the
+    counters are reset by the consumer) and back to back with other kernels in between."""
+    N = 512
+    g = torch.Generator().manual_seed(M + K + 7)
+    x, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+    r = torch.randn(M, N, generator=g)
+    gam, bet = (1 + 0.1 * torch.randn(N, generator=g)).to(DEV), (0.1 * torch.randn(N, generator=g)).to(DEV)
+    a2, w2, r2 = ops.split_bf16(x.to(DEV), M, K), ops.split_bf16(w.to(DEV), N, K), ops.split_bf16(r.to(DEV), M, N)
+    bd = b.to(DEV)
+    nwin = (M // seg) * (seg - q0) if seg else 0
+    tmp = torch.empty(M, N, device=DEV)
+    ref = torch.zeros(M, 2 * N, dtype=torch.bfloat16, device=DEV)
+    refw = torch.zeros(max(nwin, 1), 2 * N, dtype=torch.bfloat16, device=DEV)
+    ops.linear_tc(a2, w2, M, N, K, y=tmp, bias=bd, residual_split=r2)
+    if seg:
+        ops.layernorm(tmp, gam, bet, None, M, N, eps=1e-5, y2=ref, y2_win=refw, seg=seg, seg_q0=q0)
+    else:
+        ops.layernorm(tmp, gam, bet, None, M, N, eps=1e-5, y2=ref)
+    flags = torch.zeros((M + 127) // 128 + 1, dtype=torch.int32, device=DEV)
+    tmp2 = torch.empty(M, N, device=DEV)
+    for it in range(12):
+        got = torch.full((M, 2 * N), float("nan"), dtype=torch.bfloat16, device=DEV)
+        gotw = torch.full((max(nwin, 1), 2 * N), float("nan"), dtype=torch.bfloat16, device=DEV)
+        tmp2.fill_(float("nan"))
+        ops.linear_tc(a2, w2, M, N, K, y=tmp2, bias=bd, residual_split=r2, rowflags=flags)
+        ops.layernorm_flags(tmp2, gam, bet, M, N, got, flags, 4 * N, eps=1e-5, **(dict(y2_win=gotw, seg=seg, seg_q0=q0) if seg else {}))
+        if it % 3 == 0:   # another GEMM right behind (the next kernel of the trunk): it must see the LayerNorm's output complete
+            y2n = torch.zeros(M, 2 * N, dtype=torch.bfloat16, device=DEV)
+            ops.linear_tc(got, ops.split_bf16(torch.eye(N, device=DEV), N, N), M, N, N, y2=y2n, Np2=N)
+        assert torch.equal(got.view(torch.int16), ref.view(torch.int16)), it
+        if seg:
+            assert torch.equal(gotw.view(torch.int16), refw.view(torch.int16)), it
+        assert int(flags[: (M + 127) // 128].abs().sum()) == 0   # counters reset by the consumer
