@@ -46,6 +46,8 @@ class CMDMEngine:
         # measured 44.3 / 58.9 us against 34.1 / 42.8 us for GEMM + LayerNorm (profiles/r2_gemm_ln_fused_ab.txt) — its row-per-lane
         # epilogue is bound by uncoalesced residual / output accesses; parity-tested, kept for the next round
         self.fuse_ln = os.environ.get("AMB200_LN_FUSE", "0") == "1"
+        # residual add in the LayerNorm's load phase instead of the GEMM epilogue
+        self.res_in_ln = os.environ.get("AMB200_RES_IN_LN", "0") == "1"
         # LayerNorms overlapped with the GEMM in front of them through row-block flags (am_linear_tc_set_rowflags / am_layernorm_flags)
         self.ln_overlap = os.environ.get("AMB200_LN_OVERLAP", "0") == "1"
         # last encoder layer on the motion rows only (am_mha_tc_fwd_rows); needs the pipelined attention kernel
@@ -278,6 +280,17 @@ class CMDMEngine:
                     ops.linear_tc(ws["Y1S"], w[p + "w12"], Mr, self.ff, D, y2=ws["FFS"], bias=w[p + "b1"], act="gelu", Np2=ffp)
                     ops.linear_tc(ws["FFS"], w[p + "w22"], Mr, D, ffp, y=ws["TMP"], bias=w[p + "b2"], residual_split=ws["Y1S"], rowflags=ws["FLAGS"])
                     ops.layernorm_flags(ws["TMP"], w[p + "n2g"], w[p + "n2b"], Mr, D, nxtS, ws["FLAGS"], 4 * D, eps=w[p + "eps2"], **win)
+                    rs_written = rs_written or bool(win)
+                    cur, curS = nxt, nxtS
+                    continue
+                if self.res_in_ln:
+                    # the residual add moves from the GEMM epilogue (a TMA load + wait per 16-column half-block, the longest link of
+                    # the epilogue chain) into the LayerNorm's load phase: same fp32 sum in the same order, bit-identical
+                    ops.linear_tc(ws["ATTS"], w[p + "out_w2"], Mr, D, D, y=ws["TMP"], bias=w[p + "out_b"])
+                    ops.layernorm(ws["TMP"], w[p + "n1g"], w[p + "n1b"], None, Mr, D, eps=w[p + "eps1"], y2=ws["Y1S"], residual_split=resS)
+                    ops.linear_tc(ws["Y1S"], w[p + "w12"], Mr, self.ff, D, y2=ws["FFS"], bias=w[p + "b1"], act="gelu", Np2=ffp)
+                    ops.linear_tc(ws["FFS"], w[p + "w22"], Mr, D, ffp, y=ws["TMP"], bias=w[p + "b2"])
+                    ops.layernorm(ws["TMP"], w[p + "n2g"], w[p + "n2b"], None, Mr, D, eps=w[p + "eps2"], y2=nxtS, residual_split=ws["Y1S"], **win)
                     rs_written = rs_written or bool(win)
                     cur, curS = nxt, nxtS
                     continue

@@ -104,13 +104,15 @@ def linear_batched(x, w, y, M, N, K, nbatch, xb, wb, yb, bias=None, bb=0, act=No
     return y
 
 
-def layernorm(x, gamma, beta, y, M, D, residual=None, eps=1e-5, ldx=None, ldy=None, ldr=None, y2=None, y2_win=None, seg=0, seg_q0=0):
-    """y2_win: second, compact copy of rows [seg_q0, seg) of every seg-row segment of the bf16 (hi|lo) output (am_layernorm_win)."""
+def layernorm(x, gamma, beta, y, M, D, residual=None, eps=1e-5, ldx=None, ldy=None, ldr=None, y2=None, y2_win=None, seg=0, seg_q0=0,
+              residual_split=None):
+    """y2_win: second, compact copy of rows [seg_q0, seg) of every seg-row segment of the bf16 (hi|lo) output; residual_split: residual as a
+    bf16 (hi|lo) pair tensor [M, 2*pad32(D)] added as hi + lo (am_layernorm_win)."""
     _chk_cuda(x)
-    if y2_win is not None:
+    if y2_win is not None or residual_split is not None:
         _l.check(_l.load().am_layernorm_win(_ptr(x), D if ldx is None else ldx, _ptr(residual), D if ldr is None else ldr, _ptr(gamma),
                                            _ptr(beta), _ptr(y), D if ldy is None else ldy, M, D, eps, _ptr(y2), pad32(D), _ptr(y2_win),
-                                           int(seg), int(seg_q0), _stream()), "am_layernorm_win")
+                                           int(seg), int(seg_q0), _ptr(residual_split), _stream()), "am_layernorm_win")
         return y
     _l.check(_l.load().am_layernorm(_ptr(x), D if ldx is None else ldx, _ptr(residual), D if ldr is None else ldr, _ptr(gamma),
                                    _ptr(beta), _ptr(y), D if ldy is None else ldy, M, D, eps, _ptr(y2), pad32(D) if y2 is not None else 0,

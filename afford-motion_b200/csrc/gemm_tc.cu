@@ -1641,3 +1641,10 @@ extern "C" int am_linear_tc_set_rowflags(int* flags) {
     g_tc_next_rowflags = flags;
     return AM_OK;
 }
+
+// host-only view of the tail plan (tests/test_host_cpu.py checks it without a GPU)
+extern "C" int am_tc_tail_plan_(int pairs, int clusters, int* wide, int* shift) {
+    if (pairs <= 0 || clusters <= 0 || !wide || !shift) return AM_EINVAL;
+    tc_tail_plan(pairs, clusters, *wide, *shift);
+    return AM_OK;
+}

@@ -62,7 +62,8 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restr
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             float* __restrict__ Y, int ldy, int M, int D, float eps,
                                                             __nv_bfloat16* __restrict__ Y2, int Np2,
-                                                            __nv_bfloat16* __restrict__ Y2w, int seg, int seg_q0) {
+                                                            __nv_bfloat16* __restrict__ Y2w, int seg, int seg_q0,
+                                                            const __nv_bfloat16* __restrict__ R2) {
     pdl_launch_dependents();
     pdl_wait();
     int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -82,6 +83,14 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restr
     for (int i = 0; i < NV; ++i) {
         float4 t = x4[lane + 32 * i];
         if (r4) { float4 u = r4[lane + 32 * i]; t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
+        if (R2) {  // residual as a bf16 (hi | lo) pair tensor [M, 2*Np2]: t += hi + lo, the sum the GEMM epilogue used to form
+            const uint2* rh = reinterpret_cast<const uint2*>(R2 + (int64_t)row * 2 * Np2) + lane + 32 * i;
+            const uint2 h = rh[0], l = rh[Np2 / 4];
+            t.x += __uint_as_float(h.x << 16) + __uint_as_float(l.x << 16);
+            t.y += __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u);
+            t.z += __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16);
+            t.w += __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u);
+        }
         v[i] = t; s += (t.x + t.y) + (t.z + t.w);
     }
     const float mean = warp_sum(s) / (float)D;
@@ -214,7 +223,11 @@ __global__ void __launch_bounds__(256) layernorm_flag_kernel(const float* __rest
 }  // namespace
 
 extern "C" int am_layernorm_win(const float* X, int ldx, const float* R, int ldr, const float* gamma, const float* beta, float* Y, int ldy,
-                                int M, int D, float eps, void* Y2, int Np2, void* Y2w, int seg, int seg_q0, am_stream_t stream) {
+                                int M, int D, float eps, void* Y2, int Np2, void* Y2w, int seg, int seg_q0, const void* Rsplit,
+                                am_stream_t stream) {
+    AM_REQUIRE(!Rsplit || (Np2 >= D && Np2 % 32 == 0 && (reinterpret_cast<uintptr_t>(Rsplit) & 15u) == 0), AM_EINVAL,
+               "am_layernorm_win: a split residual needs Np2 (its row layout) and 16-byte alignment");
+    const __nv_bfloat16* r2 = reinterpret_cast<const __nv_bfloat16*>(Rsplit);
     AM_REQUIRE(!Y2w || (Y2 && seg > 0 && seg_q0 >= 0 && seg_q0 < seg && M % seg == 0 && (reinterpret_cast<uintptr_t>(Y2w) & 15u) == 0), AM_EINVAL,
                "am_layernorm_win: the window copy needs Y2, 0 <= seg_q0 < seg, M % seg == 0 and a 16-byte aligned Y2w");
     __nv_bfloat16* y2w = reinterpret_cast<__nv_bfloat16*>(Y2w);
@@ -225,20 +238,20 @@ extern "C" int am_layernorm_win(const float* X, int ldx, const float* R, int ldr
     int grid = cdiv(M, 8);
     auto a16 = [](const void* p_) { return (reinterpret_cast<uintptr_t>(p_) & 15u) == 0; };
     const bool vec = (D % 128 == 0) && D <= 1024 && a16(X) && (ldx % 4 == 0) && (!R || (a16(R) && ldr % 4 == 0)) && a16(gamma) && a16(beta) &&
-                     (!Y || (a16(Y) && ldy % 4 == 0)) && (!Y2 || (a16(Y2) && Np2 == D));
+                     (!Y || (a16(Y) && ldy % 4 == 0)) && (!Y2 || (a16(Y2) && Np2 == D)) && (!Rsplit || Np2 == D);
     if (vec) {
         switch (D / 128) {
-            case 1: am_launch(layernorm_vec_kernel<1>, dim3(grid), dim3(256), 0, as_stream(stream), 1, X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2, y2w, seg, seg_q0); break;
-            case 2: am_launch(layernorm_vec_kernel<2>, dim3(grid), dim3(256), 0, as_stream(stream), 1, X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2, y2w, seg, seg_q0); break;
-            case 4: am_launch(layernorm_vec_kernel<4>, dim3(grid), dim3(256), 0, as_stream(stream), 1, X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2, y2w, seg, seg_q0); break;
-            case 8: am_launch(layernorm_vec_kernel<8>, dim3(grid), dim3(256), 0, as_stream(stream), 1, X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2, y2w, seg, seg_q0); break;
+            case 1: am_launch(layernorm_vec_kernel<1>, dim3(grid), dim3(256), 0, as_stream(stream), 1, X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2, y2w, seg, seg_q0, r2); break;
+            case 2: am_launch(layernorm_vec_kernel<2>, dim3(grid), dim3(256), 0, as_stream(stream), 1, X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2, y2w, seg, seg_q0, r2); break;
+            case 4: am_launch(layernorm_vec_kernel<4>, dim3(grid), dim3(256), 0, as_stream(stream), 1, X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2, y2w, seg, seg_q0, r2); break;
+            case 8: am_launch(layernorm_vec_kernel<8>, dim3(grid), dim3(256), 0, as_stream(stream), 1, X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2, y2w, seg, seg_q0, r2); break;
             default: goto scalar_path;
         }
         AM_LAUNCH_CHECK("layernorm");
         return AM_OK;
     }
 scalar_path:
-    AM_REQUIRE(!Y2w, AM_EINVAL, "am_layernorm_win: the window copy is implemented for the vectorised path only (D % 128 == 0, aligned)");
+    AM_REQUIRE(!Y2w && !Rsplit, AM_EINVAL, "am_layernorm_win: window copy / split residual are implemented for the vectorised path only (D % 128 == 0, aligned)");
     if (D <= 256) am_launch(layernorm_kernel<8>, dim3(grid), dim3(256), 0, as_stream(stream), 1, X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2);
     else if (D <= 512) am_launch(layernorm_kernel<16>, dim3(grid), dim3(256), 0, as_stream(stream), 1, X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2);
     else am_launch(layernorm_kernel<32>, dim3(grid), dim3(256), 0, as_stream(stream), 1, X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, y2, Np2);
@@ -248,7 +261,7 @@ scalar_path:
 
 extern "C" int am_layernorm(const float* X, int ldx, const float* R, int ldr, const float* gamma, const float* beta, float* Y, int ldy,
                             int M, int D, float eps, void* Y2, int Np2, am_stream_t stream) {
-    return am_layernorm_win(X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, Y2, Np2, nullptr, 0, 0, stream);
+    return am_layernorm_win(X, ldx, R, ldr, gamma, beta, Y, ldy, M, D, eps, Y2, Np2, nullptr, 0, 0, nullptr, stream);
 }
 
 // LayerNorm overlapped with its producer GEMM (see layernorm_flag_kernel): X fp32 [M, D] (written by an am_linear_tc launch armed with

@@ -128,7 +128,9 @@ int am_layernorm(const float* X, int ldx, const float* R, int ldr, const float* 
  * go to Y2w [(M / seg) * (seg - seg_q0), 2*Np2] as well.  The LayerNorm in front of the last CMDM encoder layer writes the residual
  * stream of the motion tokens this way (models/cmdm.py:183-186 only reads those rows of the last layer). */
 int am_layernorm_win(const float* X, int ldx, const float* R, int ldr, const float* gamma, const float* beta, float* Y, int ldy,
-                     int M, int D, float eps, void* Y2, int Np2, void* Y2w, int seg, int seg_q0, am_stream_t stream);
+                     int M, int D, float eps, void* Y2, int Np2, void* Y2w, int seg, int seg_q0, const void* Rsplit, am_stream_t stream);
+/* Rsplit (optional): residual as a bf16 (hi|lo) pair tensor [M, 2*Np2] added as hi + lo before the normalisation — the residual stream
+ * in the layout the previous LayerNorm wrote it, so the GEMM in front needs no residual epilogue (same fp32 sum, same order). */
 
 /* GEMM -> LayerNorm overlap (CMDM trunk: out_proj / linear2 + residual -> norm1 / norm2, models/cmdm.py:66-77).
  * am_linear_tc_set_rowflags arms the NEXT am_linear_tc call of the calling thread (CTA-pair kernel, fp32 TMA epilogue): flags[m / 128]

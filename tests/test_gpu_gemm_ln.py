@@ -70,3 +70,25 @@ def test_layernorm_overlapped_with_its_gemm_is_bit_identical(M, K, seg, q0):
         if seg:
             assert torch.equal(gotw.view(torch.int16), refw.view(torch.int16)), it
         assert int(flags[: (M + 127) // 128].abs().sum()) == 0   # counters reset by the consumer
+
+
+@pytest.mark.parametrize("M,K", [(10432, 512), (6272, 1024), (300, 512)])
+def test_residual_added_in_layernorm_is_bit_identical(M, K):
+    """am_linear_tc without a residual + am_layernorm_win(Rsplit=...) == am_linear_tc(residual_split=...) + am_layernorm: the same fp32
+    sum (acc + bias) + (hi + lo), formed in the LayerNorm's load phase instead of the GEMM epilogue."""
+    N = 512
+    g = torch.Generator().manual_seed(M + K + 11)
+    x, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+    r = torch.randn(M, N, generator=g)
+    gam, bet = (1 + 0.1 * torch.randn(N, generator=g)).to(DEV), (0.1 * torch.randn(N, generator=g)).to(DEV)
+    a2, w2, r2 = ops.split_bf16(x.to(DEV), M, K), ops.split_bf16(w.to(DEV), N, K), ops.split_bf16(r.to(DEV), M, N)
+    bd = b.to(DEV)
+    tmp = torch.empty(M, N, device=DEV)
+    ref = torch.zeros(M, 2 * N, dtype=torch.bfloat16, device=DEV)
+    ops.linear_tc(a2, w2, M, N, K, y=tmp, bias=bd, residual_split=r2)
+    ops.layernorm(tmp, gam, bet, None, M, N, eps=1e-5, y2=ref)
+    tmp2 = torch.empty(M, N, device=DEV)
+    got = torch.zeros(M, 2 * N, dtype=torch.bfloat16, device=DEV)
+    ops.linear_tc(a2, w2, M, N, K, y=tmp2, bias=bd)
+    ops.layernorm(tmp2, gam, bet, None, M, N, eps=1e-5, y2=got, residual_split=r2)
+    assert torch.equal(got.view(torch.int16), ref.view(torch.int16))

@@ -146,3 +146,32 @@ def test_fused_adamw_and_scene_model_host_behaviour():
         load_scene_model("PointTransformerEnc", 3, 1024)
     with pytest.raises(RuntimeError):  # executing it needs the CUDA library + a GPU: CPU tensors are refused, not emulated
         seg((torch.zeros(1, 1024, 3), None))
+
+
+def test_gemm_tail_plan_covers_every_tile_once_and_never_lengthens_the_last_round():
+    """csrc/gemm_tc.cu::tc_tail_plan (host code of the CTA-pair GEMM): the remainder tiles of the last partial round are cut into
+    2^shift column pieces; every tile is covered exactly once and the estimated makespan never exceeds the uncut schedule's."""
+    import ctypes
+    from amb200 import lib
+    L = lib.load()
+    f = L.am_tc_tail_plan_
+    f.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+    cost = {0: 1.0, 1: 0.54, 2: 0.30}
+    for clusters in (74, 50, 8):
+        for pairs in range(1, 400):
+            wide, shift = ctypes.c_int(-1), ctypes.c_int(-1)
+            assert f(pairs, clusters, ctypes.byref(wide), ctypes.byref(shift)) == 0
+            w, sh = wide.value, shift.value
+            assert 0 <= w <= pairs and sh in (1, 2)
+            assert w == pairs or w % clusters == 0          # whole rounds first
+            rem = pairs - w
+            items = w + (rem << sh)
+            assert items >= pairs
+            uncut = -(-pairs // clusters)                   # rounds of whole tiles
+            planned = w // clusters + (-(-(rem << sh) // clusters)) * cost[sh] if rem else w / clusters
+            assert planned <= uncut + 1e-9, (pairs, clusters, w, sh)
+    # the trunk shapes of the headline: 82 tiles (N = 512) -> quarter pieces, 246 tiles (N = 1536) -> halves
+    for pairs, want in ((82, 2), (164, 2), (246, 1)):
+        wide, shift = ctypes.c_int(), ctypes.c_int()
+        f(pairs, 74, ctypes.byref(wide), ctypes.byref(shift))
+        assert (wide.value, shift.value) == ((pairs // 74) * 74, want)
