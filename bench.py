@@ -369,6 +369,9 @@ def main():
         flush.fill_(0.0)  # L2 flush between jobs (inside the region: ~0.1 ms per ~second-long job)
         return diff.p_sample_loop(model, (B, T, DM), clip_denoised=False, model_kwargs=kw)
 
+    out_pinned = [torch.empty(B, T, DM).pin_memory() for _ in range(2)]
+    e2e_jobs = [0]
+
     def job_e2e():
         # every job starts from HOST buffers: fresh device tensors, conditioning re-encoded by sampler_begin (never cached)
         flush.fill_(0.0)
@@ -376,7 +379,13 @@ def main():
         kw = dict(c_text=host["texts"], c_pc_xyz=pinned["xyz"].to(dev, non_blocking=True),
                   c_pc_contact=pinned["contact"].to(dev, non_blocking=True), x_mask=pinned["x_mask"].to(dev, non_blocking=True))
         out = diff.p_sample_loop(model, (B, T, DM), clip_denoised=False, model_kwargs=kw)
-        return out.to("cpu", non_blocking=False)
+        # D2H of the job's result into pinned host memory (two alternating buffers), stream-ordered: the host does not stall between jobs,
+        # so the next job's H2D copies and conditioning launches are enqueued while this job is still running; timed() synchronises
+        # after the last job, i.e. every result has landed on the host inside the timed region
+        hb = out_pinned[e2e_jobs[0] & 1]
+        e2e_jobs[0] += 1
+        hb.copy_(out, non_blocking=True)
+        return hb
 
     def barrier():
         torch.cuda.synchronize()
@@ -484,7 +493,9 @@ def main():
                           "motions_per_s": value * B / nd, "tflops_algorithmic": value * B / world * GFLOP_PER_SAMPLE_STEP / 1e3,
                           "conditioning_launches_per_job": cond_launches, "extra_legs": note or "completed"},
                 "e2e": {"value": e2e_value, "unit": "denoise-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": ms_e2e / args.steps},
+                        "ms_per_step": ms_e2e / args.steps,
+                        "copies": "per job: inputs from pinned host memory (non-blocking H2D), result into pinned host memory (stream-ordered D2H, "
+                                  "two alternating buffers); the host does not stall between jobs, the timed region ends after the last result has landed"},
                 "gpu_launches": int(launches_per_job * args.steps), "clocks": extra_now.pop("_clocks", None), "roofline": roof,
                 "cpu_baseline": extra_now.pop("_cpu_baseline", None),
                 "kernels": prof_out, "job_ms": job_ms, "graph_capture_ms_per_job": getattr(diff, "last_capture_ms", None)}
@@ -539,10 +550,17 @@ def main():
                 text_dev["t"] = t3
                 return cdiff.ddim_sample_loop(cdm, (B3, NPTS, 6), clip_denoised=False, model_kwargs=dict(c_text=texts3, c_pc_xyz=xyz3, c_pc_feat=None), eta=0.0)
 
+            out3_pinned = [torch.empty(B3, NPTS, 6).pin_memory() for _ in range(2)]
+            c3_jobs = [0]
+
             def c3_e2e():
                 text_dev["t"] = h3["text"].to(dev, non_blocking=True)
                 kw = dict(c_text=texts3, c_pc_xyz=h3["xyz"].to(dev, non_blocking=True), c_pc_feat=None)
-                return cdiff.ddim_sample_loop(cdm, (B3, NPTS, 6), clip_denoised=False, model_kwargs=kw, eta=0.0).to("cpu")
+                out3 = cdiff.ddim_sample_loop(cdm, (B3, NPTS, 6), clip_denoised=False, model_kwargs=kw, eta=0.0)
+                hb = out3_pinned[c3_jobs[0] & 1]   # stream-ordered D2H into pinned host memory, as in the headline's e2e job
+                c3_jobs[0] += 1
+                hb.copy_(out3, non_blocking=True)
+                return hb
             for _ in range(3):
                 c3_resident()
             k3 = 10
