@@ -643,7 +643,7 @@ def main():
                 loss.backward()
                 opt.all_reduce_grads()
                 opt.step()
-                last_loss["v"] = float(loss)  # D2H read of the step's result
+                last_loss["v"] = float(loss.detach())  # D2H read of the step's result
             for _ in range(3):
                 train_step()
             k4 = 8

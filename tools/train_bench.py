@@ -62,7 +62,7 @@ for it in range(steps + 2):
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
     if it >= 2:
         times.append(dt)
-    losses.append(float(loss))
+    losses.append(float(loss.detach()))
 ms = amdist.max_over_ranks(1e3 * sum(times) / len(times), device=dev)
 if rank == 0:
     print(f"CMDM training step [{mode}]: {B}/GPU x {world} GPU(s): {ms:.1f} ms/step -> {B * world / (ms / 1e3):.1f} samples/s; "
